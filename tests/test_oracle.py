@@ -1,0 +1,56 @@
+"""The oracle (oracle/papr_oracle.c, our CPU restatement) pinned against the reference's own
+outputs: tests/golden/*.out were produced by the unmodified reference binary built from
+/root/reference/papr.c (tests/golden/make_golden.py).  CPU-only."""
+import os
+
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_binding
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _gold(name, graph):
+    with open(os.path.join(GOLD, name + (".g.out" if graph else ".out")), "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_oracle_matches_reference_stdout(name, graph, manifest):
+    img = fixtures.image(name)
+    if fixtures.md5(img) != manifest[name]["input_md5"]:
+        pytest.skip("fixture generator drifted from the recorded input (numpy RNG change)")
+    assert oracle_binding.run_image(img, graph) == _gold(name, graph)
+
+
+def test_appendix_a_known_answer(manifest):
+    # language-independent golden vector
+    img = fixtures.image("appA_1M")
+    assert fixtures.md5(img) == "701a0ece11d6b9271d62debaee28aaf2"
+    assert manifest["appA_1M"]["stdout_md5.out"] == "6ceb7c9fec5b4710f57a72280ea7e060"
+    assert manifest["appA_1M"]["stdout_md5.g.out"] == "b5cbf837e98c6d348586806a4bf59ab7"
+    f = np.frombuffer(img, np.float32)
+    assert [float.hex(float(x)) for x in f[:4]] == [
+        "0x1.0cf8000000000p-5", "0x1.9bb3000000000p-3", "-0x1.4338000000000p-5", "0x1.72ec000000000p-4"]
+
+
+def test_siggen_c_twin_equals_numpy_twin():
+    for first, n, seed in [(0, 4096, 1), (2 ** 32 - 100, 300, 2), (2 ** 35 + 7, 1000, 3)]:
+        assert np.array_equal(oracle_binding.siggen(first, n, seed), fixtures.siggen(first, n, seed))
+
+
+def test_reference_binary_if_present(manifest, tmp_path):
+    """Where oracle/_ref/papr exists (it travels with the snapshot) re-run it on a few fixtures."""
+    import subprocess
+    ref = os.path.join(oracle_binding.ORACLE_DIR, "_ref", "papr")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/papr not built")
+    for name in ("appA_300k_s7", "odd_bytes_odd", "burst"):
+        p = tmp_path / (name + ".cfile")
+        p.write_bytes(fixtures.image(name))
+        for graph in (False, True):
+            r = subprocess.run([ref] + (["-g"] if graph else []) + [str(p)], capture_output=True)
+            assert r.stdout == _gold(name, graph)
