@@ -1,0 +1,116 @@
+// papr_device.cuh — device-side data layout shared by the kernels and the engine.
+//
+// HBM layout (per GPU):
+//   capture shard      float32 I/Q interleaved, exactly the file bytes (gr_complex, papr.c:101-103)
+//   warp partials      PaprWarpPartial[grid*32]   running pass-1 state of each resident warp
+//   cell histogram     u64[16384]                 samples per "cell" = float32 bit pattern >> sh
+//   ambiguity map      u32[16384]                 cell -> 1 + first fine-table counter, 0 = unambiguous
+//   fine table         u64[slots << sh]           one counter per float32 value of an ambiguous cell
+//   tables             double pow10[L], ratio_min[L] per mode (host libm, built once)
+#pragma once
+#include <stdint.h>
+#include "../../include/papr_b200.h"
+
+#define PAPR_THREADS 1024                      // threads per CTA of the scan kernels
+#define PAPR_WARPS (PAPR_THREADS / 32)
+#define PAPR_U 4                               // float4 loads in flight per lane per batch
+#define PAPR_BATCH_VEC (32 * PAPR_U)           // float4 per warp batch
+#define PAPR_BATCH_SAMPLES (2 * PAPR_BATCH_VEC)// 256 samples = 2 KiB contiguous per warp batch
+#define PAPR_NCELLS_MAX 16384                  // cells of the shared-memory histogram
+#define PAPR_SH_MIN 12                         // finest cell: 2^12 float32 values (2048 cells / octave)
+#define PAPR_SH_MAX 23
+#define PAPR_NTRACK 5                          // peak power, +I, -I, +Q, -Q
+
+// order of the five extreme trackers everywhere on the device
+enum { TR_PEAK = 0, TR_RE_POS = 1, TR_RE_NEG = 2, TR_IM_POS = 3, TR_IM_NEG = 4 };
+
+// pass-1 state of one shard (or the merge of several); papr.c:36-49
+struct PaprDevStats {
+    double sum;
+    unsigned long long n;
+    unsigned long long idx[PAPR_NTRACK]; // global sample index of the first occurrence
+    int val[PAPR_NTRACK];                // float32 bits of the magnitude (>= 0; 0 = reference's 0.0 init)
+    unsigned int flags;
+};
+
+// running pass-1 state of one warp, persistent across the chunk launches of a streamed shard
+struct PaprWarpPartial {
+    double sum;
+    unsigned long long idx[PAPR_NTRACK];
+    int val[PAPR_NTRACK];
+    unsigned int pad;
+};
+
+enum { PLAN_HIST = 1, PLAN_BSEARCH = 2 };
+
+struct PaprPlan {
+    int sh;             // cell = (float bits >> sh) - cell_base
+    int cell_base;
+    int ncells;         // <= PAPR_NCELLS_MAX
+    int n_amb;          // ambiguous cells that own a slot in the fine table
+    int status;         // PLAN_HIST: cell histogram valid; PLAN_BSEARCH: generic kernel must run instead
+    int levels_covered; // fused mode: levels whose window fits the cell range / fine table
+    float window;       // fused mode: relative half-width of the threshold windows
+    int pad;
+    double avg_pred;    // fused mode: predicted mean power
+};
+
+struct PaprDevLevels {
+    double avg;
+    double ratio;       // (double)peak / avg
+    int L;
+    int graph;
+    float level[PAPR_MAX_LEVELS];
+};
+
+// status word written by the resolve kernel
+enum { RES_MISS = 1 };
+
+struct PaprScanArgs {
+    const float *iq;               // 16-byte aligned
+    unsigned long long nsamples;   // complete samples in this launch, < 2^32
+    unsigned long long first_index;// global sample index of iq[0]
+    PaprWarpPartial *wp;           // [gridDim.x * PAPR_WARPS]
+    const PaprPlan *plan;
+    const unsigned *fine_base;     // [PAPR_NCELLS_MAX] 1 + first fine-table counter of the cell, 0 = none
+    unsigned long long *g_hist;    // [PAPR_NCELLS_MAX]
+    unsigned long long *g_fine;    // [n_amb << sh]
+    unsigned long long *g_over;    // samples above the cell range
+};
+
+// launchers (papr_kernels.cu)
+struct PaprTables {
+    const double *pow10;     // [PAPR_MAX_LEVELS] pow(10, x_j) with the host libm, x_j per papr.c:139 / 170-172
+    const double *ratio_min; // [PAPR_MAX_LEVELS] least peak/avg ratio for which the reference runs level j
+    int nlevels_max;
+};
+
+void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cudaStream_t s);
+void papr_launch_partials_reset(PaprWarpPartial *wp, int nwarps, cudaStream_t s);
+void papr_launch_stats_finalize(const PaprWarpPartial *wp, int nwarps, unsigned long long n,
+                                PaprDevStats *out, cudaStream_t s);
+void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
+                        PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s);
+void papr_launch_presample(const float *iq, unsigned long long nsamples, int stride, int grid,
+                           double *warp_pre /* [grid*PAPR_WARPS*3] */, cudaStream_t s);
+void papr_launch_presample_reduce(const double *warp_pre, int nwarps, double *pre4, cudaStream_t s);
+void papr_launch_plan_pred(const double *pre4, PaprTables t, int graph, float sigmas, int fine_slots,
+                           PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
+void papr_launch_plan_exact(const PaprDevLevels *lv, const PaprDevStats *merged, int fine_bytes_log2,
+                            PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
+void papr_launch_zero_fine(const PaprPlan *plan, unsigned long long *g_fine, int grid, cudaStream_t s);
+void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
+                         unsigned long long *g_hist /* turned into suffix sums */,
+                         const unsigned long long *g_fine, const unsigned long long *g_over,
+                         unsigned long long *counts, int *status, int grid, cudaStream_t s);
+void papr_launch_bsearch(const float *iq, unsigned long long nsamples, const PaprPlan *plan,
+                         const PaprDevLevels *lv, unsigned long long *bhist, int grid, cudaStream_t s);
+void papr_launch_bsearch_counts(const PaprPlan *plan, const PaprDevLevels *lv,
+                                const unsigned long long *bhist, unsigned long long *counts,
+                                cudaStream_t s);
+void papr_launch_siggen(float *iq, unsigned long long first, unsigned long long nsamples,
+                        unsigned long long seed, int grid, cudaStream_t s);
+void papr_launch_find_nan(const float *iq, unsigned long long nsamples, unsigned long long first_index,
+                          unsigned long long *out_idx, int grid, cudaStream_t s);
+int papr_scan_smem_bytes(bool hist);
+int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

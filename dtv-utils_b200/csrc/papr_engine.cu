@@ -1,0 +1,804 @@
+// papr_engine.cu — the C ABI (include/papr_b200.h): engine lifetime, the device-resident analysis,
+// the host-buffer analysis (pinned double-buffered H2D overlapped with the statistics pass) and the
+// per-stage entry points for sharded callers.
+//
+// One analysis is a single stream-ordered chain of launches with ONE host synchronisation at the
+// end: the reference's scalar epilogue (papr.c:131-141 / 164-173) is evaluated on the device from
+// host-libm tables (papr_levels_kernel), then re-evaluated on the host with the real libm and
+// compared bit for bit before anything is reported.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "papr_device.cuh"
+#include "papr_host.h"
+
+typedef unsigned long long u64;
+
+namespace {
+
+constexpr int kStages = 3;                 // pinned staging buffers for pageable sources
+constexpr u64 kMaxLaunchSamples = 1ull << 31;  // per scan launch (32-bit sample offsets inside a launch)
+constexpr int kLevels1dB = 256;            // table sizes: PAPR < 192.7 dB (papr_b200.h)
+constexpr int kLevelsGraph = PAPR_MAX_LEVELS;
+
+// everything one memset clears before an analysis
+struct Ctl {
+    u64 hist[PAPR_NCELLS_MAX];
+    u64 over;
+    u64 counts[PAPR_MAX_LEVELS + 1];
+    u64 bhist[PAPR_MAX_LEVELS + 1];
+    u64 nan_idx;
+    int status;
+    int pad;
+};
+
+// pinned mirror of the device results, filled by one batch of D2H copies
+struct HostOut {
+    PaprDevStats merged;
+    PaprDevStats local;
+    PaprDevLevels lv;
+    PaprPlan plan;
+    u64 counts[PAPR_MAX_LEVELS + 1];
+    u64 nan_idx;
+    int status;
+    int pad;
+    float nan_sample[2];
+    double pre4[4];
+};
+
+std::string g_create_error;
+
+// fork-join helper threads for staging pageable captures into pinned memory
+class CopyPool {
+public:
+    explicit CopyPool(int n) : stop_(false), pending_(0), gen_(0)
+    {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        if (workers_.empty() || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        {
+            std::lock_guard<std::mutex> l(m_);
+            dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes;
+            pending_ = (int)workers_.size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this] { return pending_ == 0; });
+    }
+
+private:
+    void run(int id)
+    {
+        u64 seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> l(m_);
+            cv_.wait(l, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            size_t n = workers_.size(), per = (bytes_ / n + 4095) & ~(size_t)4095;
+            size_t lo = std::min(bytes_, per * id), hi = std::min(bytes_, lo + per);
+            char *d = dst_; const char *s = src_;
+            l.unlock();
+            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            l.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    bool stop_;
+    int pending_;
+    u64 gen_;
+    char *dst_ = nullptr; const char *src_ = nullptr; size_t bytes_ = 0;
+};
+
+} // namespace
+
+struct papr_engine {
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    // tunables
+    int mode = PAPR_MODE_AUTO;
+    int presample_stride = 32;
+    float window_sigmas = 5.0f;
+    size_t chunk_bytes = 64u << 20;
+    int staging_threads = 8;
+    int grid_per_sm = 1;
+    u64 fused_min_samples = 1ull << 24;
+    int fine_bytes_log2 = 26; // 64 MiB fine table
+    // device work buffers
+    int grid = 0, nwarps = 0;
+    PaprWarpPartial *d_wp = nullptr;
+    Ctl *d_ctl = nullptr;
+    unsigned *d_fine_base = nullptr;
+    u64 *d_fine = nullptr;
+    PaprPlan *d_plan = nullptr;
+    PaprDevStats *d_stats = nullptr; // [0] local, [1] merged
+    PaprDevLevels *d_levels = nullptr;
+    double *d_pre_wp = nullptr, *d_pre4 = nullptr;
+    double *d_tables = nullptr; // pow10[2][MAX] | ratio_min[2][MAX]
+    HostOut *h_out = nullptr;
+    // host path
+    float *d_buf = nullptr;
+    size_t d_buf_bytes = 0;
+    void *h_stage[kStages] = {nullptr, nullptr, nullptr};
+    size_t h_stage_bytes = 0;
+    cudaEvent_t stage_done[kStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_ready = nullptr;
+    CopyPool *pool = nullptr;
+    // timing / accounting
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_scan[4] = {nullptr, nullptr, nullptr, nullptr};
+    int scan_pairs = 0;
+    unsigned launches = 0;
+    u64 h2d = 0, d2h = 0;
+
+    PaprTables tables(int graph) const
+    {
+        PaprTables t;
+        t.pow10 = d_tables + (graph ? PAPR_MAX_LEVELS : 0);
+        t.ratio_min = d_tables + 2 * PAPR_MAX_LEVELS + (graph ? PAPR_MAX_LEVELS : 0);
+        t.nlevels_max = graph ? kLevelsGraph : kLevels1dB;
+        return t;
+    }
+};
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+            return PAPR_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+static int fail(papr_engine *e, int code, const std::string &msg)
+{
+    e->err = msg;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int papr_abi_version(void) { return PAPR_B200_ABI_VERSION; }
+
+extern "C" const char *papr_last_error(const papr_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void *papr_engine_stream(papr_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+static int engine_init(papr_engine *e, int device)
+{
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (count == 0) return fail(e, PAPR_ERR_CUDA, "no CUDA device");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= count) return fail(e, PAPR_ERR_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    e->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(e, PAPR_ERR_CUDA, "this library is built for sm_100a (B200) only");
+    e->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    if (papr_scan_configure() != 0) return fail(e, PAPR_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed");
+    e->grid = e->num_sms * e->grid_per_sm;
+    e->nwarps = e->grid * PAPR_WARPS;
+    CU(cudaMalloc(&e->d_wp, sizeof(PaprWarpPartial) * e->nwarps));
+    CU(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
+    CU(cudaMalloc(&e->d_fine_base, sizeof(unsigned) * PAPR_NCELLS_MAX));
+    CU(cudaMalloc(&e->d_fine, (size_t)1 << e->fine_bytes_log2));
+    CU(cudaMalloc(&e->d_plan, sizeof(PaprPlan)));
+    CU(cudaMalloc(&e->d_stats, 2 * sizeof(PaprDevStats)));
+    CU(cudaMalloc(&e->d_levels, sizeof(PaprDevLevels)));
+    CU(cudaMalloc(&e->d_pre_wp, sizeof(double) * 3 * e->nwarps));
+    CU(cudaMalloc(&e->d_pre4, sizeof(double) * 4));
+    CU(cudaMalloc(&e->d_tables, sizeof(double) * 4 * PAPR_MAX_LEVELS));
+    CU(cudaHostAlloc(&e->h_out, sizeof(HostOut), cudaHostAllocDefault));
+    {
+        std::vector<double> t(4 * PAPR_MAX_LEVELS, INFINITY);
+        papr_host_build_tables(0, kLevels1dB, &t[0], &t[2 * PAPR_MAX_LEVELS]);
+        papr_host_build_tables(1, kLevelsGraph, &t[PAPR_MAX_LEVELS], &t[3 * PAPR_MAX_LEVELS]);
+        CU(cudaMemcpy(e->d_tables, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice));
+    }
+    CU(cudaEventCreate(&e->ev_begin));
+    CU(cudaEventCreate(&e->ev_end));
+    for (auto &ev : e->ev_scan) CU(cudaEventCreate(&ev));
+    for (auto &ev : e->stage_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->chunk_ready, cudaEventDisableTiming));
+    return PAPR_OK;
+}
+
+extern "C" int papr_engine_create(int device, papr_engine **out)
+{
+    if (!out) return PAPR_ERR_ARG;
+    *out = nullptr;
+    papr_engine *e = new papr_engine();
+    int rc = engine_init(e, device);
+    if (rc != PAPR_OK) {
+        g_create_error = e->err;
+        papr_engine_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return PAPR_OK;
+}
+
+extern "C" void papr_engine_destroy(papr_engine *e)
+{
+    if (!e) return;
+    delete e->pool;
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_wp); cudaFree(e->d_ctl); cudaFree(e->d_fine_base); cudaFree(e->d_fine);
+    cudaFree(e->d_plan); cudaFree(e->d_stats); cudaFree(e->d_levels); cudaFree(e->d_pre_wp);
+    cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    for (auto &p : e->h_stage) if (p) cudaFreeHost(p);
+    for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_scan) if (ev) cudaEventDestroy(ev);
+    if (e->chunk_ready) cudaEventDestroy(e->chunk_ready);
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
+{
+    if (!e || !name) return PAPR_ERR_ARG;
+    std::string n(name);
+    if (n == "mode") e->mode = (int)v;
+    else if (n == "presample_stride") e->presample_stride = std::max(1, (int)v);
+    else if (n == "window_sigmas") e->window_sigmas = (float)v;
+    else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(size_t)((PAPR_BATCH_SAMPLES * 8) - 1));
+    else if (n == "staging_threads") { e->staging_threads = std::max(0, (int)v); delete e->pool; e->pool = nullptr; }
+    else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
+    else if (n == "fine_bytes_log2") e->fine_bytes_log2 = std::min(26, std::max(4, (int)v)); // <= the allocation
+    else if (n == "grid_per_sm") return fail(e, PAPR_ERR_ARG, "grid_per_sm is fixed at engine creation");
+    else return fail(e, PAPR_ERR_ARG, "unknown tunable: " + n);
+    return PAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch chains (everything below only enqueues on e->stream)
+// ------------------------------------------------------------------------------------------------
+static int enqueue_reset(papr_engine *e)
+{
+    papr_launch_partials_reset(e->d_wp, e->nwarps, e->stream);
+    CU(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
+    CU(cudaMemsetAsync(&e->d_ctl->nan_idx, 0xff, sizeof(u64), e->stream));
+    e->launches += 1;
+    return PAPR_OK;
+}
+
+static void scan_args(papr_engine *e, PaprScanArgs &a, const float *d_iq, u64 n, u64 first)
+{
+    a.iq = d_iq;
+    a.nsamples = n;
+    a.first_index = first;
+    a.wp = e->d_wp;
+    a.plan = e->d_plan;
+    a.fine_base = e->d_fine_base;
+    a.g_hist = e->d_ctl->hist;
+    a.g_fine = e->d_fine;
+    a.g_over = &e->d_ctl->over;
+}
+
+// one pass over [d_iq, d_iq + 2n) split into launches of < 2^32 samples at batch-aligned cuts
+static int enqueue_scan(papr_engine *e, bool stats, bool hist, const float *d_iq, u64 n, u64 first, bool timed)
+{
+    if (timed && e->scan_pairs < 2) CU(cudaEventRecord(e->ev_scan[2 * e->scan_pairs], e->stream));
+    for (u64 off = 0; off < n || (off == 0 && n == 0 && stats); off += kMaxLaunchSamples) {
+        u64 m = std::min(kMaxLaunchSamples, n - off);
+        if (m == 0) break;
+        PaprScanArgs a;
+        scan_args(e, a, d_iq + 2 * off, m, first + off);
+        papr_launch_scan(stats, hist, e->grid, a, e->stream);
+        e->launches += 1;
+    }
+    if (timed && e->scan_pairs < 2) {
+        CU(cudaEventRecord(e->ev_scan[2 * e->scan_pairs + 1], e->stream));
+        e->scan_pairs++;
+    }
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+// warp partials -> local stats -> (single shard) merged stats, avg, L, levels on the device
+static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph)
+{
+    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
+    papr_launch_levels(&e->d_stats[0], 1, e->tables(graph), graph, &e->d_stats[1], e->d_levels, e->stream);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+static int enqueue_resolve(papr_engine *e)
+{
+    papr_launch_resolve(e->d_plan, e->d_fine_base, e->d_levels, e->d_ctl->hist, e->d_fine, &e->d_ctl->over,
+                        e->d_ctl->counts, &e->d_ctl->status, e->num_sms * 2, e->stream);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+// exact-threshold CCDF pass over resident data (d_levels / d_stats[1] already hold levels and peak)
+static int enqueue_hist_exact(papr_engine *e, const float *d_iq, u64 n, bool timed)
+{
+    papr_launch_plan_exact(e->d_levels, &e->d_stats[1], e->fine_bytes_log2, e->d_plan, e->d_fine_base, e->stream);
+    papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
+    e->launches += 2;
+    int rc = enqueue_scan(e, false, true, d_iq, n, 0, timed);
+    if (rc) return rc;
+    papr_launch_bsearch(d_iq, n, e->d_plan, e->d_levels, e->d_ctl->bhist, e->grid, e->stream); // no-op unless PLAN_BSEARCH
+    e->launches += 1;
+    rc = enqueue_resolve(e);
+    if (rc) return rc;
+    papr_launch_bsearch_counts(e->d_plan, e->d_levels, e->d_ctl->bhist, e->d_ctl->counts, e->stream);
+    e->launches += 1;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+static int enqueue_fetch(papr_engine *e)
+{
+    HostOut *h = e->h_out;
+    CU(cudaMemcpyAsync(&h->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&h->merged, &e->d_stats[1], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&h->lv, e->d_levels, sizeof(PaprDevLevels), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&h->plan, e->d_plan, sizeof(PaprPlan), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(h->counts, e->d_ctl->counts, sizeof(h->counts), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&h->status, &e->d_ctl->status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    e->d2h += 2 * sizeof(PaprDevStats) + sizeof(PaprDevLevels) + sizeof(PaprPlan) + sizeof(h->counts) + sizeof(int);
+    return PAPR_OK;
+}
+
+static float bits_to_float(int b)
+{
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+static void stats_to_host(const PaprDevStats &d, papr_stats *s)
+{
+    memset(s, 0, sizeof(*s));
+    s->n = d.n;
+    s->sum = d.sum;
+    s->peak = bits_to_float(d.val[TR_PEAK]);
+    s->peak_idx = d.idx[TR_PEAK];
+    s->re_pos = bits_to_float(d.val[TR_RE_POS]);
+    s->re_pos_idx = d.idx[TR_RE_POS];
+    s->im_pos = bits_to_float(d.val[TR_IM_POS]);
+    s->im_pos_idx = d.idx[TR_IM_POS];
+    // the negative trackers hold magnitudes; 0 means "never below the 0.0 initial value" (papr.c:44-45)
+    s->re_neg = d.val[TR_RE_NEG] ? -bits_to_float(d.val[TR_RE_NEG]) : 0.0f;
+    s->re_neg_idx = d.idx[TR_RE_NEG];
+    s->im_neg = d.val[TR_IM_NEG] ? -bits_to_float(d.val[TR_IM_NEG]) : 0.0f;
+    s->im_neg_idx = d.idx[TR_IM_NEG];
+    s->flags = d.flags;
+}
+
+static void stats_to_device(const papr_stats &s, PaprDevStats *d)
+{
+    auto fb = [](float f) { int b; memcpy(&b, &f, 4); return b; };
+    d->sum = s.sum;
+    d->n = s.n;
+    d->val[TR_PEAK] = fb(s.peak);       d->idx[TR_PEAK] = s.peak_idx;
+    d->val[TR_RE_POS] = fb(s.re_pos);   d->idx[TR_RE_POS] = s.re_pos_idx;
+    d->val[TR_RE_NEG] = s.re_neg < 0 ? fb(-s.re_neg) : 0; d->idx[TR_RE_NEG] = s.re_neg_idx;
+    d->val[TR_IM_POS] = fb(s.im_pos);   d->idx[TR_IM_POS] = s.im_pos_idx;
+    d->val[TR_IM_NEG] = s.im_neg < 0 ? fb(-s.im_neg) : 0; d->idx[TR_IM_NEG] = s.im_neg_idx;
+    d->flags = s.flags;
+}
+
+// ------------------------------------------------------------------------------------------------
+// completion: one synchronisation, host re-evaluation of the epilogue, verification
+// ------------------------------------------------------------------------------------------------
+// Subsample density of the fused mode: the windows around the predicted thresholds shrink with
+// 1/sqrt(subsample), and all of them must fit the fine table, so -g (0.1 dB spacing, ~10x the levels)
+// wants a 4x larger subsample than the 1 dB mode.  Capped by the "presample_stride" tunable.
+static int presample_stride_for(const papr_engine *e, u64 n, int graph)
+{
+    const u64 nbatch = n / PAPR_BATCH_SAMPLES, target = graph ? (1u << 18) : (1u << 16);
+    return (int)std::max<u64>(1, std::min<u64>((u64)e->presample_stride, nbatch / target));
+}
+
+static void begin_analysis(papr_engine *e)
+{
+    e->scan_pairs = 0;
+    e->launches = 0;
+    e->h2d = e->d2h = 0;
+    cudaSetDevice(e->device);
+}
+
+// The reference's printed "nan" carries the sign of the first NaN that entered `sum` (x86 addsd /
+// addss keep the destination operand's NaN: papr.c:103-104 compile to Q*Q + I*I and sum += value),
+// while the GPU produces a canonical NaN.  Find that sample and restore the sign.
+static int fix_nan_sign(papr_engine *e, const float *d_iq, u64 n, u64 first, papr_stats *st)
+{
+    if (!std::isnan(st->sum) || n == 0) return PAPR_OK;
+    papr_launch_find_nan(d_iq, n, first, &e->d_ctl->nan_idx, e->num_sms * 8, e->stream);
+    CU(cudaMemcpyAsync(&e->h_out->nan_idx, &e->d_ctl->nan_idx, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    u64 k = e->h_out->nan_idx;
+    if (k == ~0ull) return PAPR_OK; // Inf - Inf cannot occur (powers are >= 0); nothing to do
+    CU(cudaMemcpyAsync(e->h_out->nan_sample, d_iq + 2 * (k - first), 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    float re = e->h_out->nan_sample[0], im = e->h_out->nan_sample[1];
+    bool neg = std::isnan(im) ? std::signbit(im) : std::signbit(re);
+    st->sum = std::copysign(std::fabs(st->sum), neg ? -1.0 : 1.0);
+    e->launches += 1;
+    e->d2h += 16;
+    return PAPR_OK;
+}
+
+// Fill `out` from the fetched device results; 1 = device level table disagrees with the host libm
+// (or the fused pass missed): the caller must run the exact CCDF pass with out->level[].
+static int collect(papr_engine *e, int graph, papr_result *out, bool counts_valid)
+{
+    const HostOut *h = e->h_out;
+    papr_result_finish(out, graph);
+    int redo = 0;
+    if (out->nlevels > 0) {
+        bool same = h->lv.L == out->nlevels &&
+                    memcmp(h->lv.level, out->level, sizeof(float) * (size_t)out->nlevels) == 0;
+        if (!same || !counts_valid || (h->status & RES_MISS)) redo = 1;
+        if (!redo)
+            for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)h->counts[j];
+    }
+    return redo;
+}
+
+static int upload_levels(papr_engine *e, const float *level, int L, float peak)
+{
+    static thread_local PaprDevLevels lv;
+    static thread_local PaprDevStats ms;
+    memset(&ms, 0, sizeof(ms));
+    memcpy(&ms.val[TR_PEAK], &peak, 4);
+    lv.avg = 0; lv.ratio = 0; lv.L = L; lv.graph = 0;
+    memcpy(lv.level, level, sizeof(float) * (size_t)L);
+    // pageable -> the runtime stages these synchronously, so the thread_local sources may be reused
+    CU(cudaMemcpyAsync(e->d_levels, &lv, offsetof(PaprDevLevels, level) + sizeof(float) * (size_t)L,
+                       cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(&e->d_stats[1], &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
+    e->h2d += sizeof(float) * (size_t)L + sizeof(ms);
+    return PAPR_OK;
+}
+
+// exact CCDF pass with host-provided levels; counts land in out (used for redo and papr_ccdf_device)
+static int run_exact_ccdf(papr_engine *e, const float *d_iq, u64 n, const float *level, int L, float peak,
+                          int64_t *level_count, bool accumulate)
+{
+    int rc = upload_levels(e, level, L, peak);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
+    rc = enqueue_hist_exact(e, d_iq, n, true);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(e->h_out->counts, e->d_ctl->counts, sizeof(u64) * (size_t)L, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&e->h_out->status, &e->d_ctl->status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&e->h_out->plan, e->d_plan, sizeof(PaprPlan), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->d2h += sizeof(u64) * (size_t)L + sizeof(int);
+    if (e->h_out->status & RES_MISS) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+    for (int j = 0; j < L; ++j) {
+        if (accumulate) level_count[j] += (int64_t)e->h_out->counts[j];
+        else level_count[j] = (int64_t)e->h_out->counts[j];
+    }
+    return PAPR_OK;
+}
+
+static void finish_timing(papr_engine *e, papr_result *out)
+{
+    float ms = 0.f;
+    out->scan_ms = 0.f;
+    for (int p = 0; p < e->scan_pairs; ++p)
+        if (cudaEventElapsedTime(&ms, e->ev_scan[2 * p], e->ev_scan[2 * p + 1]) == cudaSuccess) out->scan_ms += ms;
+    if (cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end) == cudaSuccess) out->device_ms = ms;
+    out->kernel_launches = e->launches;
+    out->h2d_bytes = e->h2d;
+    out->d2h_bytes = e->d2h;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident analysis
+// ------------------------------------------------------------------------------------------------
+extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n, int graph, papr_result *out)
+{
+    if (!e || !out || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    memset(out, 0, offsetof(papr_result, level));
+    int mode = e->mode;
+    const int stride = presample_stride_for(e, n, graph);
+    if (mode == PAPR_MODE_AUTO) // fused pays off once the subsample is a small fraction of the shard
+        mode = (n >= e->fused_min_samples && stride >= 8) ? PAPR_MODE_FUSED : PAPR_MODE_TWO_PASS;
+    out->mode_used = mode;
+    int rc;
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    if ((rc = enqueue_reset(e))) return rc;
+    if (mode == PAPR_MODE_FUSED) {
+        papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES), stride,
+                              e->grid, e->d_pre_wp, e->stream);
+        papr_launch_presample_reduce(e->d_pre_wp, e->nwarps, e->d_pre4, e->stream);
+        papr_launch_plan_pred(e->d_pre4, e->tables(graph), graph, e->window_sigmas,
+                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), e->d_plan, e->d_fine_base, e->stream);
+        papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
+        e->launches += 4;
+        if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
+        if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+        if ((rc = enqueue_resolve(e))) return rc;
+    } else {
+        if ((rc = enqueue_scan(e, true, false, d_iq, n, 0, true))) return rc;
+        if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+        if ((rc = enqueue_hist_exact(e, d_iq, n, true))) return rc;
+    }
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->merged, &out->stats);
+    if ((rc = fix_nan_sign(e, d_iq, n, 0, &out->stats))) return rc;
+    if (collect(e, graph, out, true)) {
+        out->fused_miss = mode == PAPR_MODE_FUSED;
+        rc = run_exact_ccdf(e, d_iq, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
+        if (rc) return rc;
+        CU(cudaEventRecord(e->ev_end, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    finish_timing(e, out);
+    return PAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages for sharded callers
+// ------------------------------------------------------------------------------------------------
+extern "C" int papr_stats_device(papr_engine *e, const float *d_iq, uint64_t n, uint64_t first, papr_stats *out)
+{
+    if (!e || !out || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    begin_analysis(e);
+    int rc;
+    if ((rc = enqueue_reset(e))) return rc;
+    if ((rc = enqueue_scan(e, true, false, d_iq, n, first, true))) return rc;
+    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
+    e->launches += 1;
+    CU(cudaMemcpyAsync(&e->h_out->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->local, out);
+    return fix_nan_sign(e, d_iq, n, first, out);
+}
+
+extern "C" int papr_ccdf_device(papr_engine *e, const float *d_iq, uint64_t n, const float *level, int L,
+                                int64_t *level_count)
+{
+    if (!e || (n && !d_iq) || L < 0 || L > PAPR_MAX_LEVELS || (L && (!level || !level_count))) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    if (L == 0 || n == 0) return PAPR_OK;
+    for (int j = 0; j < L; ++j)
+        if (!(level[j] >= 0.0f) || (j && level[j] < level[j - 1]))
+            return fail(e, PAPR_ERR_ARG, "levels must be non-negative and non-decreasing");
+    begin_analysis(e);
+    return run_exact_ccdf(e, d_iq, n, level, L, 0.0f, level_count, true);
+}
+
+extern "C" int papr_fused_presample(papr_engine *e, const float *d_iq, uint64_t n, int graph, double pre[4])
+{
+    if (!e || !pre || (n && !d_iq)) return PAPR_ERR_ARG;
+    begin_analysis(e);
+    papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
+                          presample_stride_for(e, n, graph ? 1 : 0), e->grid, e->d_pre_wp, e->stream);
+    papr_launch_presample_reduce(e->d_pre_wp, e->nwarps, e->d_pre4, e->stream);
+    CU(cudaMemcpyAsync(e->h_out->pre4, e->d_pre4, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(pre, e->h_out->pre4, sizeof(double) * 4);
+    return PAPR_OK;
+}
+
+extern "C" int papr_fused_scan(papr_engine *e, const float *d_iq, uint64_t n, uint64_t first, const double pre[4],
+                               int graph, papr_stats *out)
+{
+    if (!e || !pre || !out || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    int rc;
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    if ((rc = enqueue_reset(e))) return rc;
+    CU(cudaMemcpyAsync(e->d_pre4, pre, sizeof(double) * 4, cudaMemcpyHostToDevice, e->stream));
+    papr_launch_plan_pred(e->d_pre4, e->tables(graph), graph, e->window_sigmas,
+                          1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), e->d_plan, e->d_fine_base, e->stream);
+    papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
+    e->launches += 2;
+    if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
+    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
+    e->launches += 1;
+    CU(cudaMemcpyAsync(&e->h_out->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->local, out);
+    return fix_nan_sign(e, d_iq, n, first, out);
+}
+
+extern "C" int papr_fused_counts(papr_engine *e, const papr_stats *merged, int graph, int64_t *level_count)
+{
+    if (!e || !merged || !level_count) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    static thread_local papr_result r;
+    r.stats = *merged;
+    papr_result_finish(&r, graph);
+    if (r.nlevels == 0) return PAPR_OK;
+    PaprDevStats ms;
+    stats_to_device(*merged, &ms);
+    CU(cudaMemcpyAsync(&e->d_stats[0], &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
+    papr_launch_levels(&e->d_stats[0], 1, e->tables(graph), graph, &e->d_stats[1], e->d_levels, e->stream);
+    e->launches += 1;
+    int rc;
+    if ((rc = enqueue_resolve(e))) return rc;
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (collect(e, graph, &r, true)) return 1; // miss: caller runs papr_ccdf_device on every shard
+    for (int j = 0; j < r.nlevels; ++j) level_count[j] += r.level_count[j];
+    return PAPR_OK;
+}
+
+extern "C" int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first, uint64_t n, uint64_t seed)
+{
+    if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
+    cudaSetDevice(e->device);
+    papr_launch_siggen(d_iq, first, n, seed, e->num_sms * 16, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return PAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer analysis: chunked H2D (direct from pinned sources, through a pinned staging ring filled
+// by helper threads for pageable ones), statistics pass per chunk as it lands, shard kept resident
+// in HBM so the CCDF pass never touches PCIe again.
+// ------------------------------------------------------------------------------------------------
+static int ensure_device_buffer(papr_engine *e, size_t bytes)
+{
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (bytes <= e->d_buf_bytes) return PAPR_OK;
+    if (e->d_buf) { cudaFree(e->d_buf); e->d_buf = nullptr; e->d_buf_bytes = 0; }
+    CU(cudaMalloc(&e->d_buf, bytes));
+    e->d_buf_bytes = bytes;
+    return PAPR_OK;
+}
+
+static int ensure_staging(papr_engine *e)
+{
+    if (e->h_stage_bytes != e->chunk_bytes) {
+        for (auto &p : e->h_stage) { if (p) cudaFreeHost(p); p = nullptr; }
+        for (auto &p : e->h_stage) CU(cudaHostAlloc(&p, e->chunk_bytes, cudaHostAllocDefault));
+        e->h_stage_bytes = e->chunk_bytes;
+    }
+    if (!e->pool) e->pool = new CopyPool(e->staging_threads);
+    return PAPR_OK;
+}
+
+extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t bytes, int graph, papr_result *out)
+{
+    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    memset(out, 0, offsetof(papr_result, level));
+    out->mode_used = PAPR_MODE_TWO_PASS;
+    const unsigned char *img = (const unsigned char *)image;
+    const u64 nfloats = bytes / 4, npairs = nfloats / 2;
+    const bool tail = (nfloats & 1) != 0;
+    const u64 n = npairs + (tail ? 1 : 0); // papr.c:102: a lone trailing I still counts as a sample
+    int rc;
+    if ((rc = ensure_device_buffer(e, n * 8 + 16))) return rc;
+
+    cudaPointerAttributes attr;
+    bool pinned = bytes && cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && npairs && (rc = ensure_staging(e))) return rc;
+
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    if ((rc = enqueue_reset(e))) return rc;
+    float tail_pair[2] = {0.f, 0.f};
+    if (tail) {
+        memcpy(&tail_pair[0], img + 4 * (nfloats - 1), 4);
+        tail_pair[1] = papr_host_stale_q(img, bytes);
+    }
+    const u64 chunk_samples = e->chunk_bytes / 8;
+    int stage = 0;
+    for (u64 off = 0; off < n || off == 0; off += chunk_samples) {
+        const u64 m = std::min(chunk_samples, n - off);        // samples of this chunk (incl. the tail sample)
+        const u64 mp = std::min(m, npairs > off ? npairs - off : 0); // complete pairs to copy from the image
+        if (mp) {
+            const void *src = img + off * 8;
+            if (!pinned) {
+                CU(cudaEventSynchronize(e->stage_done[stage])); // ring slot free again?
+                e->pool->copy(e->h_stage[stage], src, mp * 8);
+                src = e->h_stage[stage];
+            }
+            CU(cudaMemcpyAsync(e->d_buf + 2 * off, src, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
+            if (!pinned) {
+                CU(cudaEventRecord(e->stage_done[stage], e->copy_stream));
+                stage = (stage + 1) % kStages;
+            }
+            e->h2d += mp * 8;
+        }
+        if (tail && off + m == n) {
+            CU(cudaMemcpyAsync(e->d_buf + 2 * npairs, tail_pair, 8, cudaMemcpyHostToDevice, e->copy_stream));
+            e->h2d += 8;
+        }
+        CU(cudaEventRecord(e->chunk_ready, e->copy_stream));
+        CU(cudaStreamWaitEvent(e->stream, e->chunk_ready, 0));
+        if (m && (rc = enqueue_scan(e, true, false, e->d_buf + 2 * off, m, off, false))) return rc;
+        if (n == 0) break;
+    }
+    if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+    if ((rc = enqueue_hist_exact(e, e->d_buf, n, true))) return rc;
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->merged, &out->stats);
+    if ((rc = fix_nan_sign(e, e->d_buf, n, 0, &out->stats))) return rc;
+    if (collect(e, graph, out, true)) {
+        rc = run_exact_ccdf(e, e->d_buf, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
+        if (rc) return rc;
+        CU(cudaEventRecord(e->ev_end, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    finish_timing(e, out);
+    return PAPR_OK;
+}
+
+extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)
+{
+    if (!e || !path || !out) return PAPR_ERR_ARG;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(e, PAPR_ERR_IO, std::string("cannot open ") + path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return fail(e, PAPR_ERR_IO, "fstat failed"); }
+    size_t bytes = (size_t)sb.st_size;
+    void *img = nullptr;
+    if (bytes) {
+        img = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (img == MAP_FAILED) { close(fd); return fail(e, PAPR_ERR_IO, "mmap failed"); }
+        madvise(img, bytes, MADV_SEQUENTIAL | MADV_WILLNEED);
+    }
+    int rc = papr_analyze_host(e, img, bytes, graph, out);
+    if (img) munmap(img, bytes);
+    close(fd);
+    return rc;
+}

@@ -1,0 +1,830 @@
+// papr_kernels.cu — hand-written sm_100a kernels of the PAPR/CCDF hot path.
+//
+// What the reference does per sample (drmpeg/dtv-utils papr.c):
+//   pass 1  papr.c:100-129   v = I*I + Q*Q (three separately rounded float32 ops), sum += v (double),
+//                            strict-> first-occurrence maxima of v, +I, -I, +Q, -Q
+//   pass 2  papr.c:143-153   for every level j: if (v > level[j]) level_count[j]++      (O(N*L))
+//           papr.c:175-185   same with 0.1 dB levels (-g)
+//
+// How it is done here (HBM-bound byte/float work, no tensor cores):
+//   * one persistent grid (2 CTAs x 512 threads per SM); a warp owns 2 KiB-contiguous "batches"
+//     (32 lanes x 4 x 16-byte streaming loads in flight per lane), batches ascend per warp so a
+//     strict compare keeps the first occurrence;
+//   * extremes: per-lane FMNMX into batch maxima, one REDUX.MAX per tracker per batch, and only on the
+//     (warp-uniform, rare) improvement a REDUX.MIN locates the exact sample - no per-lane index state;
+//   * sum: per-lane double accumulation, fixed-order shuffle tree, per-warp partials reduced in a
+//     fixed order by a 1-CTA follow-up kernel (deterministic run to run);
+//   * CCDF: the O(N*L) compare loop is replaced by a histogram of "cells" (float32 bit pattern >> sh,
+//     i.e. 2048 log-spaced cells per octave) in shared memory; only samples whose cell contains a
+//     threshold (or, in the fused mode, may contain it) are additionally counted exactly, one counter
+//     per float32 value, in a small L2-resident fine table.  level_count[j] = samples in cells above
+//     the threshold's cell + the fine counters above the threshold inside its cell.  Exact.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "papr_device.cuh"
+
+#define FULL 0xffffffffu
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+// 16-byte streaming load: read-only path, do not allocate in L1 (every byte is used exactly once)
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(p));
+    return r;
+}
+
+// papr.c:103 — (I*I)+(Q*Q) with each operation rounded to float32 (the canonical x86-64 build of
+// the reference emits mulss, mulss, addss; an FMA here changes the printed percentages)
+__device__ __forceinline__ float power_of(float i, float q)
+{
+    return __fadd_rn(__fmul_rn(i, i), __fmul_rn(q, q));
+}
+
+template <int T>
+__device__ __forceinline__ void track_vals(const float4 &q, float v0, float v1, float &a, float &b)
+{
+    if (T == TR_PEAK) { a = v0; b = v1; }
+    if (T == TR_RE_POS) { a = q.x; b = q.z; }
+    if (T == TR_RE_NEG) { a = -q.x; b = -q.z; }
+    if (T == TR_IM_POS) { a = q.y; b = q.w; }
+    if (T == TR_IM_NEG) { a = -q.y; b = -q.w; }
+}
+
+__device__ __forceinline__ double warp_sum_fixed(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+    return x; // lane 0 holds the total; same association order every run
+}
+
+// (value desc, index asc): lower index wins ties = the reference's strict compare in file order
+__device__ __forceinline__ bool better(int va, u64 ia, int vb, u64 ib)
+{
+    return va > vb || (va == vb && ia < ib);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the scan kernel: pass 1 (STATS), pass 2 (HIST) or both in one sweep over the shard
+// ------------------------------------------------------------------------------------------------
+// dynamic shared memory of the scan kernel: u32 hist[NCELLS_MAX+1] | u32 fine_base[NCELLS_MAX+1]
+// (cell NCELLS_MAX is the overflow cell: samples above the planned range)
+extern __shared__ __align__(16) unsigned char scan_smem[];
+#define SCAN_SMEM_BYTES (8 * (PAPR_NCELLS_MAX + 1))
+
+template <bool STATS, bool HIST>
+struct ScanState {
+    // pass 1
+    double dsum;
+    int run_val[PAPR_NTRACK];
+    unsigned run_pos[PAPR_NTRACK]; // sample offset inside this launch of the current first occurrence
+    unsigned upd;
+    // pass 2
+    u64 *g_fine;
+    unsigned smem_hist; // shared-window byte address of hist[0]
+    int sh, cell_base, ncells;
+    unsigned fmask;
+};
+
+// One sample of the CCDF pass.  Branch-free up to the (warp-level infrequent) fine-table update:
+// cell index clamped into the overflow cell, predicated shared-memory reduction + lookup of the
+// cell's fine-table base (0 = no threshold can lie in this cell).
+template <bool STATS, bool HIST>
+__device__ __forceinline__ void hist_one(ScanState<STATS, HIST> &st, float v)
+{
+    const unsigned bits = __float_as_uint(v);
+    const int d = min((int)(bits >> st.sh) - st.cell_base, st.ncells);
+    const unsigned addr = st.smem_hist + ((unsigned)d << 2);
+    unsigned fb = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ge.s32 p, %1, 0;\n\t"
+        "@p red.shared.add.u32 [%2], 1;\n\t"
+        "@p ld.shared.u32 %0, [%2+%3];\n\t}"
+        : "+r"(fb)
+        : "r"(d), "r"(addr), "n"(4 * (PAPR_NCELLS_MAX + 1))
+        : "memory");
+    if (fb) atomicAdd(&st.g_fine[fb - 1u + (bits & st.fmask)], 1ull);
+}
+
+template <int T, bool STATS, bool HIST>
+__device__ __forceinline__ void track_update(ScanState<STATS, HIST> &st, const float4 (&r)[PAPR_U],
+                                             float bm, unsigned batch_off, int lane)
+{
+    int w = __reduce_max_sync(FULL, __float_as_int(bm));
+    if (w > st.run_val[T]) { // warp-uniform and rare: locate the first sample of the batch equal to w
+        unsigned pos = 0xffffffffu;
+#pragma unroll
+        for (int u = PAPR_U - 1; u >= 0; --u) {
+            float v0 = power_of(r[u].x, r[u].y), v1 = power_of(r[u].z, r[u].w), a, b;
+            track_vals<T>(r[u], v0, v1, a, b);
+            unsigned p = 2u * (unsigned)(u * 32 + lane);
+            if (__float_as_int(b) == w) pos = p + 1;
+            if (__float_as_int(a) == w) pos = p;
+        }
+        pos = __reduce_min_sync(FULL, pos);
+        st.run_val[T] = w;
+        st.run_pos[T] = batch_off + pos;
+        st.upd |= 1u << T;
+    }
+}
+
+template <bool STATS, bool HIST>
+__device__ __forceinline__ void process_batch(ScanState<STATS, HIST> &st, const float4 (&r)[PAPR_U],
+                                              unsigned batch_off, int lane, bool do_hist)
+{
+    float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
+#pragma unroll
+    for (int u = 0; u < PAPR_U; ++u) {
+        const float4 q = r[u];
+        float v0 = power_of(q.x, q.y);
+        float v1 = power_of(q.z, q.w);
+        if (STATS) {
+            st.dsum += (double)v0; // papr.c:104 (order differs from the file order)
+            st.dsum += (double)v1;
+            // fmaxf drops NaN operands, like the reference's comparisons (papr.c:105-126)
+            bm0 = fmaxf(bm0, fmaxf(v0, v1));
+            bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
+            bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
+            bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
+            bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
+        }
+        if (HIST && do_hist) {
+            hist_one(st, v0);
+            hist_one(st, v1);
+        }
+    }
+    if (STATS) {
+        track_update<TR_PEAK>(st, r, bm0, batch_off, lane);
+        track_update<TR_RE_POS>(st, r, bm1, batch_off, lane);
+        track_update<TR_RE_NEG>(st, r, bm2, batch_off, lane);
+        track_update<TR_IM_POS>(st, r, bm3, batch_off, lane);
+        track_update<TR_IM_NEG>(st, r, bm4, batch_off, lane);
+    }
+}
+
+template <bool STATS, bool HIST>
+__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprScanArgs a)
+{
+    ScanState<STATS, HIST> st;
+    unsigned *s_hist = reinterpret_cast<unsigned *>(scan_smem);
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = blockIdx.x * PAPR_WARPS + (threadIdx.x >> 5);
+    const unsigned GW = gridDim.x * PAPR_WARPS;
+    bool do_hist = false;
+
+    if (HIST) {
+        const PaprPlan pl = *a.plan;
+        do_hist = (pl.status & PLAN_HIST) != 0;
+        if (!STATS && !do_hist) return;
+        unsigned *s_fb = s_hist + (PAPR_NCELLS_MAX + 1);
+        st.g_fine = a.g_fine;
+        // opaque to the optimiser on purpose: otherwise the window base is rematerialised per sample
+        asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
+                     : "=r"(st.smem_hist) : "l"(s_hist));
+        st.sh = pl.sh;
+        st.cell_base = pl.cell_base;
+        st.ncells = do_hist ? pl.ncells : 0;
+        st.fmask = (1u << pl.sh) - 1u;
+        if (do_hist) {
+            for (int i = threadIdx.x; i <= st.ncells; i += PAPR_THREADS) {
+                s_hist[i] = 0;
+                s_fb[i] = i < st.ncells ? a.fine_base[i] : 0u;
+            }
+        }
+        __syncthreads();
+    }
+    if (STATS) {
+        st.dsum = 0.0;
+        st.upd = 0;
+#pragma unroll
+        for (int t = 0; t < PAPR_NTRACK; ++t) {
+            st.run_val[t] = a.wp[gw].val[t]; // carried across the chunk launches of a streamed shard
+            st.run_pos[t] = 0;
+        }
+    }
+
+    const float4 *p = reinterpret_cast<const float4 *>(a.iq);
+    const unsigned nbatch_full = (unsigned)(a.nsamples / PAPR_BATCH_SAMPLES);
+    for (unsigned b = gw; b < nbatch_full; b += GW) {
+        const float4 *q = p + (size_t)b * PAPR_BATCH_VEC + lane;
+        float4 r[PAPR_U];
+#pragma unroll
+        for (int u = 0; u < PAPR_U; ++u) r[u] = ldg_stream(q + 32 * u);
+        process_batch(st, r, b * PAPR_BATCH_SAMPLES, lane, do_hist);
+    }
+    // ragged last batch (zero padded: zeros add +0.0 to the sum, beat no maximum, exceed no threshold)
+    const u64 done = (u64)nbatch_full * PAPR_BATCH_SAMPLES;
+    if (done < a.nsamples && gw == nbatch_full % GW) {
+        float4 r[PAPR_U];
+#pragma unroll
+        for (int u = 0; u < PAPR_U; ++u) {
+            u64 s0 = done + 2u * (unsigned)(u * 32 + lane);
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + 1 < a.nsamples) {
+                r[u] = ldg_stream(p + (s0 >> 1));
+            } else if (s0 < a.nsamples) {
+                float2 t = *reinterpret_cast<const float2 *>(a.iq + 2 * s0);
+                r[u].x = t.x;
+                r[u].y = t.y;
+            }
+        }
+        process_batch(st, r, (unsigned)done, lane, do_hist);
+    }
+
+    if (STATS) {
+        double wsum = warp_sum_fixed(st.dsum);
+        if (lane == 0) {
+            PaprWarpPartial *w = a.wp + gw;
+            w->sum += wsum;
+#pragma unroll
+            for (int t = 0; t < PAPR_NTRACK; ++t)
+                if (st.upd & (1u << t)) {
+                    w->val[t] = st.run_val[t];
+                    w->idx[t] = a.first_index + st.run_pos[t];
+                }
+        }
+    }
+    if (HIST && do_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < st.ncells; i += PAPR_THREADS) {
+            unsigned c = s_hist[i];
+            if (c) atomicAdd(&a.g_hist[i], (u64)c);
+        }
+        if (threadIdx.x == 0 && s_hist[st.ncells]) atomicAdd(a.g_over, (u64)s_hist[st.ncells]);
+    }
+}
+
+int papr_scan_smem_bytes(bool hist) { return hist ? SCAN_SMEM_BYTES : 0; }
+
+int papr_scan_configure(void)
+{
+    int smem = papr_scan_smem_bytes(true);
+    cudaError_t e1 = cudaFuncSetAttribute(papr_scan_kernel<true, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e2 = cudaFuncSetAttribute(papr_scan_kernel<false, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
+}
+
+void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cudaStream_t s)
+{
+    if (stats && hist)
+        papr_scan_kernel<true, true><<<grid, PAPR_THREADS, papr_scan_smem_bytes(true), s>>>(a);
+    else if (stats)
+        papr_scan_kernel<true, false><<<grid, PAPR_THREADS, 0, s>>>(a);
+    else
+        papr_scan_kernel<false, true><<<grid, PAPR_THREADS, papr_scan_smem_bytes(true), s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass-1 follow-ups
+// ------------------------------------------------------------------------------------------------
+__global__ void papr_partials_reset_kernel(PaprWarpPartial *wp, int nwarps)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nwarps) {
+        PaprWarpPartial z;
+        z.sum = 0.0;
+        z.pad = 0;
+        for (int t = 0; t < PAPR_NTRACK; ++t) { z.idx[t] = 0; z.val[t] = 0; } // papr.c:37-49 zero init
+        wp[i] = z;
+    }
+}
+
+void papr_launch_partials_reset(PaprWarpPartial *wp, int nwarps, cudaStream_t s)
+{
+    papr_partials_reset_kernel<<<(nwarps + 255) / 256, 256, 0, s>>>(wp, nwarps);
+}
+
+#define FIN_T 256
+// one CTA: fixed-order reduction of the warp partials (sum) and (value desc, index asc) selection
+__global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprWarpPartial *wp, int nwarps,
+                                                                   u64 n, PaprDevStats *out)
+{
+    __shared__ double s_sum[FIN_T];
+    __shared__ int s_val[PAPR_NTRACK][FIN_T];
+    __shared__ u64 s_idx[PAPR_NTRACK][FIN_T];
+    const int t = threadIdx.x;
+    double sum = 0.0;
+    int val[PAPR_NTRACK];
+    u64 idx[PAPR_NTRACK];
+    for (int k = 0; k < PAPR_NTRACK; ++k) { val[k] = 0; idx[k] = 0; }
+    for (int i = t; i < nwarps; i += FIN_T) {
+        sum += wp[i].sum;
+        for (int k = 0; k < PAPR_NTRACK; ++k)
+            if (wp[i].val[k] > 0 && better(wp[i].val[k], wp[i].idx[k], val[k], idx[k])) {
+                val[k] = wp[i].val[k];
+                idx[k] = wp[i].idx[k];
+            }
+    }
+    s_sum[t] = sum;
+    for (int k = 0; k < PAPR_NTRACK; ++k) { s_val[k][t] = val[k]; s_idx[k][t] = idx[k]; }
+    __syncthreads();
+    for (int o = FIN_T / 2; o > 0; o >>= 1) {
+        if (t < o) {
+            s_sum[t] += s_sum[t + o];
+            for (int k = 0; k < PAPR_NTRACK; ++k)
+                if (s_val[k][t + o] > 0 && better(s_val[k][t + o], s_idx[k][t + o], s_val[k][t], s_idx[k][t])) {
+                    s_val[k][t] = s_val[k][t + o];
+                    s_idx[k][t] = s_idx[k][t + o];
+                }
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        out->sum = s_sum[0];
+        out->n = n;
+        for (int k = 0; k < PAPR_NTRACK; ++k) { out->val[k] = s_val[k][0]; out->idx[k] = s_idx[k][0]; }
+        out->flags = isfinite(s_sum[0]) ? 0u : PAPR_FLAG_NONFINITE;
+    }
+}
+
+void papr_launch_stats_finalize(const PaprWarpPartial *wp, int nwarps, u64 n, PaprDevStats *out,
+                                cudaStream_t s)
+{
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nwarps, n, out);
+}
+
+// Merge the shards' pass-1 states in rank (= index) order and evaluate the reference's scalar
+// epilogue on the device:  avg = sum/offset (papr.c:131), ratio = peak/avg, L, and
+// level[j] = (float)(pow(10, x_j) * avg) (papr.c:139 / 170).  pow(10, x_j) and the least ratio for
+// which the reference's loops reach level j are tabulated once with the HOST libm, so only IEEE
+// double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
+__global__ void papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb, int graph,
+                                   PaprDevStats *merged, PaprDevLevels *lv)
+{
+    __shared__ int s_L;
+    __shared__ double s_avg;
+    if (threadIdx.x == 0) {
+        PaprDevStats m = parts[0];
+        for (int p = 1; p < nparts; ++p) {
+            const PaprDevStats q = parts[p];
+            m.sum += q.sum;
+            m.n += q.n;
+            for (int k = 0; k < PAPR_NTRACK; ++k)
+                if (q.val[k] > m.val[k]) { m.val[k] = q.val[k]; m.idx[k] = q.idx[k]; } // strict: earlier shard wins ties
+            m.flags |= q.flags;
+        }
+        if (!isfinite(m.sum)) m.flags |= PAPR_FLAG_NONFINITE;
+        *merged = m;
+        double avg = __ddiv_rn(m.sum, (double)(long long)m.n);
+        double ratio = __ddiv_rn((double)__int_as_float(m.val[TR_PEAK]), avg);
+        int lo = 0, hi = tb.nlevels_max; // number of j with ratio >= ratio_min[j] (non-decreasing table)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (ratio >= tb.ratio_min[mid]) lo = mid + 1; else hi = mid;
+        }
+        lv->avg = avg;
+        lv->ratio = ratio;
+        lv->L = lo;
+        lv->graph = graph;
+        s_L = lo;
+        s_avg = avg;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < s_L; j += blockDim.x)
+        lv->level[j] = __double2float_rn(__dmul_rn(tb.pow10[j], s_avg));
+}
+
+void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
+                        PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s)
+{
+    papr_levels_kernel<<<1, 256, 0, s>>>(parts, nparts, t, graph, merged, lv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused mode: strided subsample -> predicted mean and its standard error
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// Every `stride`-th warp batch (at a hashed position inside its group, so a periodic capture cannot
+// alias with the stride).  Per warp: sum, sum of squares and count of the *batch* sums - batch means
+// give an honest standard error even when neighbouring samples are correlated.
+__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_presample_kernel(const float *iq, u64 nsamples,
+                                                                         int stride, double *warp_pre)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = blockIdx.x * PAPR_WARPS + (threadIdx.x >> 5);
+    const unsigned GW = gridDim.x * PAPR_WARPS;
+    const unsigned nbatch = (unsigned)(nsamples / PAPR_BATCH_SAMPLES);
+    const unsigned ngroups = (nbatch + stride - 1) / stride;
+    const float4 *p = reinterpret_cast<const float4 *>(iq);
+    double s1 = 0.0, s2 = 0.0, cnt = 0.0;
+    for (unsigned g = gw; g < ngroups; g += GW) {
+        unsigned b = g * stride + hash32(g) % stride;
+        if (b >= nbatch) continue;
+        const float4 *q = p + (size_t)b * PAPR_BATCH_VEC + lane;
+        float4 r[PAPR_U];
+#pragma unroll
+        for (int u = 0; u < PAPR_U; ++u) r[u] = ldg_stream(q + 32 * u);
+        double ls = 0.0;
+#pragma unroll
+        for (int u = 0; u < PAPR_U; ++u) {
+            ls += (double)power_of(r[u].x, r[u].y);
+            ls += (double)power_of(r[u].z, r[u].w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL, ls, o);
+        s1 += ls;
+        s2 += ls * ls;
+        cnt += 1.0;
+    }
+    if (lane == 0) {
+        warp_pre[3 * gw + 0] = s1;
+        warp_pre[3 * gw + 1] = s2;
+        warp_pre[3 * gw + 2] = cnt;
+    }
+}
+
+void papr_launch_presample(const float *iq, u64 nsamples, int stride, int grid, double *warp_pre,
+                           cudaStream_t s)
+{
+    papr_presample_kernel<<<grid, PAPR_THREADS, 0, s>>>(iq, nsamples, stride, warp_pre);
+}
+
+__global__ void __launch_bounds__(1024) papr_presample_reduce_kernel(const double *warp_pre, int nwarps,
+                                                                     double *pre4)
+{
+    __shared__ double s[3][1024];
+    const int t = threadIdx.x;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int i = t; i < nwarps; i += 1024) {
+        a0 += warp_pre[3 * i]; a1 += warp_pre[3 * i + 1]; a2 += warp_pre[3 * i + 2];
+    }
+    s[0][t] = a0; s[1][t] = a1; s[2][t] = a2;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (t < o) { s[0][t] += s[0][t + o]; s[1][t] += s[1][t + o]; s[2][t] += s[2][t + o]; }
+        __syncthreads();
+    }
+    if (t == 0) { pre4[0] = s[0][0]; pre4[1] = s[1][0]; pre4[2] = s[2][0]; pre4[3] = 0.0; }
+}
+
+void papr_launch_presample_reduce(const double *warp_pre, int nwarps, double *pre4, cudaStream_t s)
+{
+    papr_presample_reduce_kernel<<<1, 1024, 0, s>>>(warp_pre, nwarps, pre4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans: which cells exist and which of them need exact (per-value) counting
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of s_flag[0..PAPR_NCELLS_MAX) by one 1024-thread CTA; writes fine_base[] =
+// 1 + (slot << sh), the cell's first counter in the fine table, or 0 for an unambiguous cell
+__device__ int assign_slots(const unsigned char *s_flag, int ncells, int sh, int max_slots, unsigned *fine_base,
+                            int *s_scan /* [1024] */)
+{
+    const int t = threadIdx.x;
+    const int per = PAPR_NCELLS_MAX / 1024;
+    int local = 0;
+    for (int k = 0; k < per; ++k) {
+        int c = t * per + k;
+        local += (c < ncells && s_flag[c]) ? 1 : 0;
+    }
+    s_scan[t] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan
+        int v = (t >= o) ? s_scan[t - o] : 0;
+        __syncthreads();
+        s_scan[t] += v;
+        __syncthreads();
+    }
+    int ord = s_scan[t] - local;
+    for (int k = 0; k < per; ++k) {
+        int c = t * per + k;
+        unsigned fb = 0;
+        if (c < ncells && s_flag[c]) {
+            if (ord < max_slots) fb = ((unsigned)ord << sh) + 1u;
+            ord++;
+        }
+        fine_base[c] = fb;
+    }
+    int total = s_scan[1023];
+    __syncthreads();
+    return total < max_slots ? total : max_slots;
+}
+
+// Fused mode.  pre4 = {sum, sum of squares, count} of batch sums (already reduced over ranks).
+__global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, PaprTables tb, float sigmas,
+                                                              int fine_slots, PaprPlan *plan,
+                                                              unsigned *fine_base)
+{
+    __shared__ unsigned char s_flag[PAPR_NCELLS_MAX];
+    __shared__ int s_scan[1024];
+    __shared__ int s_cov;
+    const int t = threadIdx.x;
+    const double s1 = pre4[0], s2 = pre4[1], cnt = pre4[2];
+    PaprPlan pl;
+    pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
+    pl.levels_covered = 0; pl.window = 0.f; pl.pad = 0; pl.avg_pred = 0.0;
+    const bool ok = cnt >= 16.0 && s1 > 0.0 && isfinite(s1) && isfinite(s2);
+    if (!ok) { // nothing to predict from: the exact pass will run
+        for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) fine_base[c] = 0;
+        if (t == 0) *plan = pl;
+        return;
+    }
+    const double mean_b = s1 / cnt;
+    double var_b = (s2 / cnt - mean_b * mean_b) * cnt / (cnt - 1.0);
+    if (!(var_b > 0.0)) var_b = 0.0;
+    const double se_rel = sqrt(var_b / cnt) / mean_b;
+    const double w = (double)sigmas * se_rel + 0x1p-18; // floor: a few float32 ulps of the thresholds
+    const double avg = mean_b / (double)PAPR_BATCH_SAMPLES;
+    const int sh = PAPR_SH_MIN;
+    float lo0 = __double2float_rd(avg * (1.0 - w));
+    if (!(lo0 > 0.f)) lo0 = 0.f;
+    const int base = (int)(__float_as_uint(lo0) >> sh);
+    const int ncells = PAPR_NCELLS_MAX;
+    for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) s_flag[c] = 0;
+    if (t == 0) s_cov = tb.nlevels_max;
+    __syncthreads();
+    // which levels have their whole window inside the cell range
+    for (int j = t; j < tb.nlevels_max; j += 1024) {
+        float hi = __double2float_ru(tb.pow10[j] * avg * (1.0 + w));
+        int chi = isfinite(hi) ? (int)(__float_as_uint(hi) >> sh) - base : ncells;
+        if (chi >= ncells) atomicMin(&s_cov, j);
+    }
+    __syncthreads();
+    const int cov = s_cov;
+    for (int j = t; j < cov; j += 1024) {
+        float lo = __double2float_rd(tb.pow10[j] * avg * (1.0 - w));
+        float hi = __double2float_ru(tb.pow10[j] * avg * (1.0 + w));
+        if (!(lo > 0.f)) lo = 0.f;
+        int clo = (int)(__float_as_uint(lo) >> sh) - base, chi = (int)(__float_as_uint(hi) >> sh) - base;
+        if (clo < 0) clo = 0;
+        for (int c = clo; c <= chi; ++c) s_flag[c] = 1;
+    }
+    __syncthreads();
+    int n_amb = assign_slots(s_flag, ncells, sh, fine_slots, fine_base, s_scan);
+    if (t == 0) {
+        pl.sh = sh; pl.cell_base = base; pl.ncells = ncells; pl.n_amb = n_amb; pl.status = PLAN_HIST;
+        pl.levels_covered = cov; pl.window = (float)w; pl.avg_pred = avg;
+        *plan = pl;
+    }
+}
+
+void papr_launch_plan_pred(const double *pre4, PaprTables t, int graph, float sigmas, int fine_slots,
+                           PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
+{
+    (void)graph;
+    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, t, sigmas, fine_slots, plan, fine_base);
+}
+
+// Exact thresholds known (two-pass mode, or redo after a fused miss): ambiguous = the cells that hold
+// a threshold.  Picks the finest cell size whose range [min level, max(level, peak)] fits.
+__global__ void __launch_bounds__(1024) papr_plan_exact_kernel(const PaprDevLevels *lv, const PaprDevStats *merged,
+                                                               int fine_bytes_log2, PaprPlan *plan,
+                                                               unsigned *fine_base)
+{
+    __shared__ unsigned char s_flag[PAPR_NCELLS_MAX];
+    __shared__ int s_scan[1024];
+    __shared__ unsigned s_lo, s_hi;
+    const int t = threadIdx.x;
+    const int L = lv->L;
+    PaprPlan pl;
+    pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
+    pl.levels_covered = L; pl.window = 0.f; pl.pad = 0; pl.avg_pred = lv->avg;
+    if (L <= 0) {
+        for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) fine_base[c] = 0;
+        if (t == 0) *plan = pl;
+        return;
+    }
+    if (t == 0) { s_lo = 0xffffffffu; s_hi = (unsigned)merged->val[TR_PEAK]; }
+    for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) s_flag[c] = 0;
+    __syncthreads();
+    for (int j = t; j < L; j += 1024) { // levels are >= +0.0: float order == unsigned bit order
+        unsigned b = __float_as_uint(lv->level[j]);
+        atomicMin(&s_lo, b);
+        atomicMax(&s_hi, b);
+    }
+    __syncthreads();
+    int sh = PAPR_SH_MIN;
+    while (sh < PAPR_SH_MAX && (int)((s_hi >> sh) - (s_lo >> sh)) + 1 > PAPR_NCELLS_MAX) ++sh;
+    const int base = (int)(s_lo >> sh);
+    const int ncells = (int)(s_hi >> sh) - base + 1;
+    for (int j = t; j < L; j += 1024) s_flag[(int)(__float_as_uint(lv->level[j]) >> sh) - base] = 1;
+    __syncthreads();
+    int n_amb = assign_slots(s_flag, ncells, sh, (1 << (31 - sh)) - 1, fine_base, s_scan);
+    if (t == 0) {
+        pl.sh = sh; pl.cell_base = base; pl.ncells = ncells; pl.n_amb = n_amb;
+        // fine table needs n_amb * 2^sh counters of 8 bytes
+        bool fits = ((unsigned long long)n_amb << (sh + 3)) <= (1ull << fine_bytes_log2);
+        pl.status = fits ? PLAN_HIST : PLAN_BSEARCH;
+        *plan = pl;
+    }
+}
+
+void papr_launch_plan_exact(const PaprDevLevels *lv, const PaprDevStats *merged, int fine_bytes_log2,
+                            PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
+{
+    papr_plan_exact_kernel<<<1, 1024, 0, s>>>(lv, merged, fine_bytes_log2, plan, fine_base);
+}
+
+__global__ void papr_zero_fine_kernel(const PaprPlan *plan, ulonglong2 *g_fine)
+{
+    const PaprPlan pl = *plan;
+    if (!(pl.status & PLAN_HIST)) return;
+    const size_t n2 = ((size_t)pl.n_amb << pl.sh) >> 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+        g_fine[i] = make_ulonglong2(0ull, 0ull);
+}
+
+void papr_launch_zero_fine(const PaprPlan *plan, u64 *g_fine, int grid, cudaStream_t s)
+{
+    papr_zero_fine_kernel<<<grid, 512, 0, s>>>(plan, reinterpret_cast<ulonglong2 *>(g_fine));
+}
+
+// ------------------------------------------------------------------------------------------------
+// resolve: cell histogram + fine table + exact thresholds -> level_count   (papr.c:147-151 restated)
+// ------------------------------------------------------------------------------------------------
+// g_hist[c] := number of samples in cells > c   (one CTA)
+__global__ void __launch_bounds__(1024) papr_suffix_kernel(const PaprPlan *plan, u64 *g_hist)
+{
+    __shared__ u64 s_scan[1024];
+    const PaprPlan pl = *plan;
+    if (!(pl.status & PLAN_HIST)) return;
+    const int t = threadIdx.x;
+    const int per = PAPR_NCELLS_MAX / 1024;
+    u64 v[PAPR_NCELLS_MAX / 1024];
+    u64 local = 0;
+    for (int k = 0; k < per; ++k) {
+        int c = t * per + k;
+        v[k] = c < pl.ncells ? g_hist[c] : 0;
+        local += v[k];
+    }
+    s_scan[t] = local;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // inclusive scan from the top: s_scan[t] = sum of threads >= t
+        u64 x = (t + o < 1024) ? s_scan[t + o] : 0;
+        __syncthreads();
+        s_scan[t] += x;
+        __syncthreads();
+    }
+    u64 above = s_scan[t] - local; // cells owned by higher threads
+    for (int k = per - 1; k >= 0; --k) {
+        int c = t * per + k;
+        if (c < pl.ncells) g_hist[c] = above;
+        above += v[k];
+    }
+}
+
+// one CTA per level (grid-stride): counts[j] = over + suffix[cell(T_j)] + sum of fine counters of the
+// values of that cell that are > T_j.  A threshold outside the planned cells / windows => RES_MISS.
+__global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, const unsigned *fine_base,
+                                                         const PaprDevLevels *lv, const u64 *g_suffix,
+                                                         const u64 *g_fine, const u64 *g_over, u64 *counts,
+                                                         int *status)
+{
+    __shared__ u64 s_red[256];
+    const PaprPlan pl = *plan;
+    const int L = lv->L;
+    if (pl.status & PLAN_BSEARCH) return; // the generic kernel produced the counts
+    for (int j = blockIdx.x; j < L; j += gridDim.x) {
+        unsigned tb = __float_as_uint(lv->level[j]);
+        int d = (int)(tb >> pl.sh) - pl.cell_base;
+        bool in = (pl.status & PLAN_HIST) && (unsigned)d < (unsigned)pl.ncells;
+        unsigned fb = in ? fine_base[d] : 0;
+        if (!fb) {
+            if (threadIdx.x == 0) { atomicOr(status, RES_MISS); counts[j] = 0; }
+            continue;
+        }
+        const unsigned fmask = (1u << pl.sh) - 1u;
+        const u64 *f = g_fine + (fb - 1u);
+        u64 acc = 0;
+        for (unsigned k = (tb & fmask) + 1 + threadIdx.x; k <= fmask; k += 256) acc += f[k];
+        s_red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) counts[j] = s_red[0] + g_suffix[d] + *g_over;
+        __syncthreads();
+    }
+}
+
+void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
+                         u64 *g_hist, const u64 *g_fine, const u64 *g_over, u64 *counts, int *status,
+                         int grid, cudaStream_t s)
+{
+    papr_suffix_kernel<<<1, 1024, 0, s>>>(plan, g_hist);
+    papr_count_kernel<<<grid, 256, 0, s>>>(plan, fine_base, lv, g_hist, g_fine, g_over, counts, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic CCDF kernel (any level table that is non-decreasing): per-sample binary search.
+// Runs only when the exact plan does not fit the fine table (PLAN_BSEARCH) - e.g. PAPR > ~100 dB.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_bsearch_kernel(const float *iq, u64 nsamples,
+                                                                       const PaprPlan *plan,
+                                                                       const PaprDevLevels *lv, u64 *bhist)
+{
+    __shared__ float s_level[PAPR_MAX_LEVELS];
+    __shared__ unsigned s_h[PAPR_MAX_LEVELS + 1];
+    if (!(plan->status & PLAN_BSEARCH)) return;
+    const int L = lv->L;
+    for (int i = threadIdx.x; i <= L; i += PAPR_THREADS) {
+        s_h[i] = 0;
+        if (i < L) s_level[i] = lv->level[i];
+    }
+    __syncthreads();
+    const float2 *p = reinterpret_cast<const float2 *>(iq);
+    for (u64 i = (u64)blockIdx.x * PAPR_THREADS + threadIdx.x; i < nsamples; i += (u64)gridDim.x * PAPR_THREADS) {
+        float2 q = p[i];
+        float v = power_of(q.x, q.y);
+        int lo = 0, hi = L; // c(v) = #{j : level[j] < v}
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (s_level[mid] < v) lo = mid + 1; else hi = mid;
+        }
+        if (lo) atomicAdd(&s_h[lo], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= L; i += PAPR_THREADS)
+        if (s_h[i]) atomicAdd(&bhist[i], (u64)s_h[i]);
+}
+
+void papr_launch_bsearch(const float *iq, u64 nsamples, const PaprPlan *plan, const PaprDevLevels *lv,
+                         u64 *bhist, int grid, cudaStream_t s)
+{
+    papr_bsearch_kernel<<<grid, PAPR_THREADS, 0, s>>>(iq, nsamples, plan, lv, bhist);
+}
+
+// counts[j] = sum_{k > j} bhist[k]   (one thread; L <= 2048)
+__global__ void papr_bsearch_counts_kernel(const PaprPlan *plan, const PaprDevLevels *lv, const u64 *bhist,
+                                           u64 *counts)
+{
+    if (!(plan->status & PLAN_BSEARCH)) return;
+    u64 above = 0;
+    for (int j = lv->L - 1; j >= 0; --j) {
+        above += bhist[j + 1];
+        counts[j] = above;
+    }
+}
+
+void papr_launch_bsearch_counts(const PaprPlan *plan, const PaprDevLevels *lv, const u64 *bhist, u64 *counts,
+                                cudaStream_t s)
+{
+    papr_bsearch_counts_kernel<<<1, 1, 0, s>>>(plan, lv, bhist, counts);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic capture generator, bit-identical to its C and numpy twins
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mix64(u64 z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ float siggen_component(u64 idx, unsigned c, u64 seed)
+{
+    int s = -262140;
+#pragma unroll
+    for (unsigned w = 0; w < 2; ++w) {
+        u64 z = mix64((4 * idx + 2 * c + w + 1) * 0x9E3779B97F4A7C15ULL + seed);
+        s += (int)((z & 0xffff) + ((z >> 16) & 0xffff) + ((z >> 32) & 0xffff) + (z >> 48));
+    }
+    return (float)s * 0x1p-19f;
+}
+
+__global__ void papr_siggen_kernel(float2 *iq, u64 first, u64 nsamples, u64 seed)
+{
+    for (u64 k = (u64)blockIdx.x * blockDim.x + threadIdx.x; k < nsamples; k += (u64)gridDim.x * blockDim.x)
+        iq[k] = make_float2(siggen_component(first + k, 0, seed), siggen_component(first + k, 1, seed));
+}
+
+void papr_launch_siggen(float *iq, u64 first, u64 nsamples, u64 seed, int grid, cudaStream_t s)
+{
+    papr_siggen_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float2 *>(iq), first, nsamples, seed);
+}
+
+// first sample whose power is NaN (the sign of the reference's printed "nan" follows that sample)
+__global__ void papr_find_nan_kernel(const float *iq, u64 nsamples, u64 first_index, u64 *out_idx)
+{
+    const float2 *p = reinterpret_cast<const float2 *>(iq);
+    u64 best = ~0ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < nsamples; i += (u64)gridDim.x * blockDim.x) {
+        float2 q = p[i];
+        float v = power_of(q.x, q.y);
+        if (v != v) { best = first_index + i; break; }
+    }
+    if (best != ~0ull) atomicMin(out_idx, best);
+}
+
+void papr_launch_find_nan(const float *iq, u64 nsamples, u64 first_index, u64 *out_idx, int grid,
+                          cudaStream_t s)
+{
+    papr_find_nan_kernel<<<grid, 256, 0, s>>>(iq, nsamples, first_index, out_idx);
+}

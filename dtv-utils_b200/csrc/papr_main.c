@@ -1,0 +1,79 @@
+/*
+ * papr_main.c — the process boundary of the reference tool (drmpeg/dtv-utils papr.c:32-98,192-195):
+ * same argv surface, same stderr texts, same exit statuses; the number crunching goes to the GPU
+ * engine and the text comes from papr_format().  There is deliberately NO CPU fallback: without a
+ * usable B200 the tool fails loudly.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/papr_b200.h"
+
+static void usage(void)
+{
+    fprintf(stderr, "usage: papr -g <infile>\n"); /* papr.c:54-56, 86-88 */
+    fprintf(stderr, "Options:\n");
+    fprintf(stderr, "\tg = graph suitable output\n");
+}
+
+int papr_main(int argc, char **argv)
+{
+    int graph = 0;
+    const char *path;
+    if (argc != 2 && argc != 3) { /* papr.c:53-58 */
+        usage();
+        return 255; /* exit(-1) */
+    }
+    if (argc == 2) {
+        path = argv[1]; /* papr.c:59-67 (even if it is literally "-g") */
+    } else {
+        if (argv[1][0] != '-') { /* papr.c:84-91 */
+            usage();
+            return 255;
+        }
+        for (size_t i = 1; i < strlen(argv[1]); i++) { /* papr.c:70-83 */
+            if (argv[1][i] == 'g' || argv[1][i] == 'G')
+                graph = 1;
+            else
+                fprintf(stderr, "Unsupported Option: %c\n", argv[1][i]); /* warn and continue */
+        }
+        path = argv[2];
+    }
+    FILE *fp = fopen(path, "r"); /* papr.c:62-66 / 93-97: same check, same message */
+    if (fp == NULL) {
+        fprintf(stderr, "Cannot open bitstream file <%s>\n", path);
+        return 255;
+    }
+    fclose(fp);
+
+    papr_engine *e = NULL;
+    const char *dev = getenv("PAPR_B200_DEVICE");
+    if (papr_engine_create(dev ? atoi(dev) : -1, &e) != PAPR_OK) {
+        fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_last_error(NULL));
+        return 1;
+    }
+    const char *v;
+    if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
+    if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
+
+    papr_result *r = (papr_result *)calloc(1, sizeof(*r));
+    int rc = papr_analyze_file(e, path, graph, r);
+    if (rc != PAPR_OK) {
+        fprintf(stderr, "papr: %s\n", papr_last_error(e));
+        papr_engine_destroy(e);
+        free(r);
+        return 1;
+    }
+    size_t cap = 256 + (size_t)r->nlevels * 64 + 1024;
+    char *text = (char *)malloc(cap);
+    long len = papr_format(r, text, cap);
+    if (len > 0) fwrite(text, 1, (size_t)len, stdout);
+    if ((v = getenv("PAPR_B200_STATS")))
+        fprintf(stderr, "papr_b200: device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n", r->device_ms, r->scan_ms,
+                r->kernel_launches, (unsigned long long)r->h2d_bytes);
+    free(text);
+    free(r);
+    papr_engine_destroy(e);
+    return 0;
+}

@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference tool's interface over the C ABI (include/papr_b200.h).
+
+The reference (drmpeg/dtv-utils papr.c) is a C program whose whole interface is
+`papr [-g] <infile>` -> stdout; `main()` below is that interface, `Engine` exposes the stages that
+the reference's `main` inlines (papr.c:100-129 statistics, :131-141/:164-173 levels, :143-153/:175-185
+CCDF counts, :132-135,154-161,186-190 text).  Everything numeric happens in libpapr_b200.so (CUDA);
+this file only marshals pointers.  There is no CPU fallback: without the library or a GPU it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+from typing import Optional, Sequence
+
+from .build import build, lib_path
+
+MAX_LEVELS = 2048
+MODE_AUTO, MODE_TWO_PASS, MODE_FUSED = 0, 1, 2
+FLAG_NONFINITE = 1
+
+
+class PaprError(RuntimeError):
+    pass
+
+
+class PaprStats(C.Structure):
+    """papr_stats: state of the reference's first loop (papr.c:36-49) for one contiguous range."""
+    _fields_ = [("n", C.c_uint64), ("sum", C.c_double), ("peak", C.c_float), ("re_pos", C.c_float),
+                ("im_pos", C.c_float), ("re_neg", C.c_float), ("im_neg", C.c_float), ("flags", C.c_uint32),
+                ("peak_idx", C.c_uint64), ("re_pos_idx", C.c_uint64), ("im_pos_idx", C.c_uint64),
+                ("re_neg_idx", C.c_uint64), ("im_neg_idx", C.c_uint64)]
+
+    def as_tuple(self):
+        return tuple(getattr(self, f) for f, _ in self._fields_)
+
+
+class PaprResult(C.Structure):
+    """papr_result: everything the reference prints, plus diagnostics."""
+    _fields_ = [("stats", PaprStats), ("avg", C.c_double), ("papr", C.c_float), ("graph", C.c_int32),
+                ("nlevels", C.c_int32), ("level", C.c_float * MAX_LEVELS),
+                ("level_count", C.c_int64 * MAX_LEVELS), ("mode_used", C.c_int32), ("fused_miss", C.c_int32),
+                ("device_ms", C.c_float), ("scan_ms", C.c_float), ("kernel_launches", C.c_uint32),
+                ("reserved", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+    def counts(self):
+        return [self.level_count[j] for j in range(self.nlevels)]
+
+    def levels(self):
+        return [self.level[j] for j in range(self.nlevels)]
+
+
+_lib = None
+
+# every symbol include/papr_b200.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", "papr_last_error",
+               "papr_engine_stream", "papr_engine_set", "papr_main", "papr_analyze_host",
+               "papr_analyze_device", "papr_analyze_file", "papr_stats_device", "papr_stats_merge",
+               "papr_levels", "papr_ccdf_device", "papr_fused_presample", "papr_fused_scan",
+               "papr_fused_counts", "papr_format", "papr_result_finish", "papr_siggen_device"]
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libpapr_b200.so (building it first if the sources are newer) and declare prototypes."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or build()
+    if not os.path.exists(p):
+        raise PaprError(f"{p} is missing: run __graft_entry__.build() (nvcc, sm_100a)")
+    lib = C.CDLL(p)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    lib.papr_abi_version.restype = i32
+    lib.papr_engine_create.argtypes = [i32, C.POINTER(vp)]
+    lib.papr_engine_destroy.argtypes = [vp]
+    lib.papr_engine_destroy.restype = None
+    lib.papr_last_error.argtypes = [vp]
+    lib.papr_last_error.restype = C.c_char_p
+    lib.papr_engine_stream.argtypes = [vp]
+    lib.papr_engine_stream.restype = vp
+    lib.papr_engine_set.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.papr_main.argtypes = [i32, C.POINTER(C.c_char_p)]
+    lib.papr_analyze_host.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
+    lib.papr_analyze_device.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
+    lib.papr_analyze_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(PaprResult)]
+    lib.papr_stats_device.argtypes = [vp, vp, u64, u64, C.POINTER(PaprStats)]
+    lib.papr_stats_merge.argtypes = [C.POINTER(PaprStats), C.POINTER(PaprStats)]
+    lib.papr_stats_merge.restype = None
+    lib.papr_levels.argtypes = [C.POINTER(PaprStats), i32, C.POINTER(C.c_double), C.POINTER(C.c_float),
+                                C.POINTER(C.c_float), i32]
+    lib.papr_ccdf_device.argtypes = [vp, vp, u64, C.POINTER(C.c_float), i32, C.POINTER(C.c_int64)]
+    lib.papr_fused_presample.argtypes = [vp, vp, u64, i32, C.POINTER(C.c_double)]
+    lib.papr_fused_scan.argtypes = [vp, vp, u64, u64, C.POINTER(C.c_double), i32, C.POINTER(PaprStats)]
+    lib.papr_fused_counts.argtypes = [vp, C.POINTER(PaprStats), i32, C.POINTER(C.c_int64)]
+    lib.papr_format.argtypes = [C.POINTER(PaprResult), C.c_char_p, C.c_size_t]
+    lib.papr_format.restype = C.c_long
+    lib.papr_result_finish.argtypes = [C.POINTER(PaprResult), i32]
+    lib.papr_siggen_device.argtypes = [vp, vp, u64, u64, u64]
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(x) -> int:
+    """Device/host address of a torch tensor, numpy array, ctypes buffer or a plain int."""
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    return C.addressof(x)
+
+
+# ---- host-only stages (no GPU needed) ---------------------------------------------------------------
+def merge_stats(parts: Sequence[PaprStats]) -> PaprStats:
+    """Fold per-range states in index order (first occurrence wins ties, papr.c:105-126)."""
+    lib = load_library()
+    acc = PaprStats.from_buffer_copy(bytes(parts[0]))
+    for p in parts[1:]:
+        lib.papr_stats_merge(C.byref(acc), C.byref(p))
+    return acc
+
+
+def levels(stats: PaprStats, graph: bool):
+    """(avg, papr, [levels]) exactly as papr.c:131-141 / :164-173 evaluate them."""
+    lib = load_library()
+    avg, papr = C.c_double(), C.c_float()
+    buf = (C.c_float * MAX_LEVELS)()
+    L = lib.papr_levels(C.byref(stats), int(bool(graph)), C.byref(avg), C.byref(papr), buf, MAX_LEVELS)
+    return avg.value, papr.value, [buf[j] for j in range(L)]
+
+
+def format_result(res: PaprResult) -> bytes:
+    """The reference's stdout for this result (papr.c:132-135,154-161 / 186-190)."""
+    lib = load_library()
+    cap = 4096 + 64 * max(res.nlevels, 0)
+    out = C.create_string_buffer(cap)
+    n = lib.papr_format(C.byref(res), out, cap)
+    if n < 0:
+        raise PaprError("papr_format failed")
+    return out.raw[:n]
+
+
+def result_from_parts(stats: PaprStats, graph: bool, counts: Sequence[int]) -> PaprResult:
+    lib = load_library()
+    res = PaprResult()
+    res.stats = stats
+    lib.papr_result_finish(C.byref(res), int(bool(graph)))
+    for j in range(res.nlevels):
+        res.level_count[j] = int(counts[j])
+    return res
+
+
+# ---- the engine ------------------------------------------------------------------------------------
+class Engine:
+    """One GPU's PAPR/CCDF engine (papr_engine).  Not thread-safe; one per GPU per thread."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.papr_engine_create(device, C.byref(h))
+        if rc != 0:
+            raise PaprError(f"papr_engine_create failed ({rc}): {self.lib.papr_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.papr_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise PaprError(f"{what} failed ({rc}): {self.lib.papr_last_error(self.h).decode()}")
+        return rc
+
+    def set(self, name: str, value: float):
+        self._check(self.lib.papr_engine_set(self.h, name.encode(), float(value)), "papr_engine_set")
+
+    @property
+    def stream(self) -> int:
+        return self.lib.papr_engine_stream(self.h) or 0
+
+    # whole analysis ------------------------------------------------------------------------------
+    def analyze_device(self, d_iq, nsamples: int, graph: bool = False) -> PaprResult:
+        res = PaprResult()
+        self._check(self.lib.papr_analyze_device(self.h, _ptr(d_iq), nsamples, int(bool(graph)), C.byref(res)),
+                    "papr_analyze_device")
+        return res
+
+    def analyze_host(self, image, nbytes: Optional[int] = None, graph: bool = False) -> PaprResult:
+        """`image` = the capture's file image: bytes, numpy array, torch CPU (pinned) tensor or address."""
+        keep = None
+        if isinstance(image, (bytes, bytearray)):
+            nbytes = len(image) if nbytes is None else nbytes
+            keep = (C.c_char * max(len(image), 1)).from_buffer_copy(image if image else b"\0")
+            addr = C.addressof(keep)
+        else:
+            if nbytes is None:
+                nbytes = image.numel() * image.element_size() if hasattr(image, "numel") else image.nbytes
+            addr = _ptr(image)
+        res = PaprResult()
+        self._check(self.lib.papr_analyze_host(self.h, addr, nbytes, int(bool(graph)), C.byref(res)),
+                    "papr_analyze_host")
+        del keep
+        return res
+
+    def analyze_file(self, path: str, graph: bool = False) -> PaprResult:
+        res = PaprResult()
+        self._check(self.lib.papr_analyze_file(self.h, os.fsencode(path), int(bool(graph)), C.byref(res)),
+                    "papr_analyze_file")
+        return res
+
+    # stages (sharded callers) --------------------------------------------------------------------
+    def stats_shard(self, d_iq, nsamples: int, first_index: int = 0) -> PaprStats:
+        st = PaprStats()
+        self._check(self.lib.papr_stats_device(self.h, _ptr(d_iq), nsamples, first_index, C.byref(st)),
+                    "papr_stats_device")
+        return st
+
+    def ccdf_shard(self, d_iq, nsamples: int, level: Sequence[float]):
+        L = len(level)
+        lv = (C.c_float * max(L, 1))(*level)
+        cnt = (C.c_int64 * max(L, 1))()
+        self._check(self.lib.papr_ccdf_device(self.h, _ptr(d_iq), nsamples, lv, L, cnt), "papr_ccdf_device")
+        return [cnt[j] for j in range(L)]
+
+    def fused_presample(self, d_iq, nsamples: int, graph: bool = False):
+        pre = (C.c_double * 4)()
+        self._check(self.lib.papr_fused_presample(self.h, _ptr(d_iq), nsamples, int(bool(graph)), pre),
+                    "papr_fused_presample")
+        return [pre[i] for i in range(4)]
+
+    def fused_scan(self, d_iq, nsamples: int, first_index: int, pre: Sequence[float], graph: bool) -> PaprStats:
+        st = PaprStats()
+        p = (C.c_double * 4)(*pre)
+        self._check(self.lib.papr_fused_scan(self.h, _ptr(d_iq), nsamples, first_index, p, int(bool(graph)),
+                                             C.byref(st)), "papr_fused_scan")
+        return st
+
+    def fused_counts(self, merged: PaprStats, graph: bool):
+        """-> (miss, counts).  miss=True: thresholds fell outside the predicted windows on this shard."""
+        cnt = (C.c_int64 * MAX_LEVELS)()
+        rc = self._check(self.lib.papr_fused_counts(self.h, C.byref(merged), int(bool(graph)), cnt),
+                         "papr_fused_counts")
+        return rc == 1, cnt
+
+    def siggen(self, d_out, first_index: int, nsamples: int, seed: int):
+        self._check(self.lib.papr_siggen_device(self.h, _ptr(d_out), first_index, nsamples, seed),
+                    "papr_siggen_device")
+
+
+# ---- byte-range sharding over ranks (one process per GPU, torch.distributed) -----------------------
+def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, mode: int = MODE_TWO_PASS,
+                    group=None) -> PaprResult:
+    """Each rank holds samples [first_index, first_index+nsamples) of one capture; ranks are in index
+    order.  Two tiny exchanges, no data-path collective: all-gather of the pass-1 states (merged in
+    rank order on every rank, so first occurrences and the level table are identical everywhere) and
+    one all-reduce (sum) of the integer level counts.  Returns the whole-capture result on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    backend = dist.get_backend(group) if dist.is_initialized() else "none"
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    graph = bool(graph)
+
+    def allreduce_f64(vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        dist.all_reduce(t, group=group)
+        return t.tolist()
+
+    def gather_stats(st: PaprStats):
+        if world == 1:
+            return [st]
+        raw = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8).to(dev)
+        out = [torch.empty_like(raw) for _ in range(world)]
+        dist.all_gather(out, raw, group=group)
+        return [PaprStats.from_buffer_copy(bytes(o.cpu().numpy().tobytes())) for o in out]
+
+    def allreduce_counts(cnt, extra=0):
+        vals = [int(c) for c in cnt] + [int(extra)]
+        if world == 1:
+            return vals[:-1], vals[-1]
+        t = torch.tensor(vals, dtype=torch.int64, device=dev)
+        dist.all_reduce(t, group=group)
+        v = t.tolist()
+        return v[:-1], v[-1]
+
+    if mode == MODE_FUSED:
+        pre = allreduce_f64(engine.fused_presample(d_iq, nsamples, graph))
+        local = engine.fused_scan(d_iq, nsamples, first_index, pre, graph)
+    else:
+        local = engine.stats_shard(d_iq, nsamples, first_index)
+    merged = merge_stats(gather_stats(local))
+    _avg, _papr, lv = levels(merged, graph)
+    L = len(lv)
+    counts = [0] * L
+    if L:
+        miss = 1
+        if mode == MODE_FUSED:
+            m, cnt = engine.fused_counts(merged, graph)
+            counts, miss = allreduce_counts([cnt[j] for j in range(L)], int(m))
+        if miss:  # two-pass mode, or some rank's thresholds fell outside its predicted windows
+            counts, _ = allreduce_counts(engine.ccdf_shard(d_iq, nsamples, lv))
+    return result_from_parts(merged, graph, counts)
+
+
+# ---- the process boundary --------------------------------------------------------------------------
+def main(argv: Optional[Sequence[str]] = None) -> int:
+    """`papr [-g] <infile>` — same argv surface, stdout/stderr text and exit status as papr.c:32-196."""
+    lib = load_library()
+    args = list(sys.argv if argv is None else argv)
+    arr = (C.c_char_p * (len(args) + 1))(*[os.fsencode(a) for a in args], None)
+    sys.stdout.flush()
+    rc = lib.papr_main(len(args), arr)
+    C.CDLL(None).fflush(None)
+    return rc

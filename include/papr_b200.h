@@ -1,0 +1,149 @@
+/*
+ * papr_b200.h — C ABI of the B200-native PAPR/CCDF engine (libpapr_b200.so).
+ *
+ * The reference tool (drmpeg/dtv-utils papr.c) has no library/plugin/FFI API: its only boundary
+ * is the process, `int main(int argc, char **argv)` (papr.c:32) with the command line
+ * `papr [-g] <infile>` (papr.c:53-98) and the text it prints (papr.c:132-135,154-161,186-190).
+ * `papr_main` below IS that boundary.  The remaining entry points expose, step by step, the
+ * stages that `main` inlines, so that a host in any language can bind them:
+ * every declaration cites the reference lines it replaces.
+ *
+ * Conventions: plain pointers and sizes only; 0 = success, negative = error (text via
+ * papr_last_error); one engine per GPU and per calling thread; "device" pointers are CUDA device
+ * addresses on the engine's GPU, 16-byte aligned; a "sample" is one float32 I/Q pair (8 bytes,
+ * the gr_complex file format, papr.c:101-103).  Sample indices are 0-based positions in the
+ * capture; the reference prints index*8 as a byte offset (papr.c:133,160-161).
+ */
+#ifndef PAPR_B200_H
+#define PAPR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAPR_B200_ABI_VERSION 1
+/* sum >= peak, so peak/avg <= N < 2^64 and PAPR < 192.7 dB: at most 1927 levels in -g mode */
+#define PAPR_MAX_LEVELS 2048
+
+enum {
+    PAPR_OK = 0,
+    PAPR_ERR_CUDA = -1,     /* CUDA runtime / driver failure (no GPU, OOM, launch error) */
+    PAPR_ERR_ARG = -2,      /* bad argument (alignment, size, NULL) */
+    PAPR_ERR_IO = -3,       /* cannot open / map the capture */
+    PAPR_ERR_INTERNAL = -4, /* self-check failed (device/host level tables disagree) */
+};
+
+/* How the CCDF pass is scheduled against the statistics pass. */
+enum {
+    PAPR_MODE_AUTO = 0,    /* fused for large inputs, two-pass for small ones */
+    PAPR_MODE_TWO_PASS = 1,/* stats pass, then histogram pass with the exact thresholds (16 B/sample) */
+    PAPR_MODE_FUSED = 2,   /* one pass: thresholds predicted from a subsample, verified a posteriori,
+                              automatic two-pass redo on a miss (~8.3 B/sample) */
+};
+
+/* State of the reference's first loop (papr.c:36-49,100-129) for one contiguous range of the
+ * capture.  Ranges merge associatively in index order (papr_stats_merge). */
+typedef struct papr_stats {
+    uint64_t n;           /* offset: samples accumulated                    papr.c:37,127 */
+    double   sum;         /* sum of float32 powers, as a double             papr.c:39,104 */
+    float    peak;        /* largest I*I+Q*Q, 0.0 if none > 0               papr.c:40,105-108 */
+    float    re_pos;      /* peak_real_pos                                  papr.c:42,110-113 */
+    float    im_pos;      /* peak_imag_pos                                  papr.c:43,119-122 */
+    float    re_neg;      /* peak_real_neg                                  papr.c:44,114-117 */
+    float    im_neg;      /* peak_imag_neg                                  papr.c:45,123-126 */
+    uint32_t flags;       /* PAPR_FLAG_* */
+    uint64_t peak_idx;    /* first sample index attaining each extreme (0 if none) papr.c:38,46-49 */
+    uint64_t re_pos_idx, im_pos_idx, re_neg_idx, im_neg_idx;
+} papr_stats;
+
+#define PAPR_FLAG_NONFINITE 1u /* sum is NaN/Inf: no CCDF lines are printed (papr.c:136-141 with NaN) */
+
+/* Everything the reference prints. */
+typedef struct papr_result {
+    papr_stats stats;
+    double   avg;                          /* sum / offset                  papr.c:131,164 */
+    float    papr;                         /* 10*log10(peak/avg) as float   papr.c:134,165 */
+    int32_t  graph;                        /* -g given                      papr.c:75-78 */
+    int32_t  nlevels;                      /* (int)papr+1 or (int)(papr*10)+1, 0 if the loops do not run */
+    float    level[PAPR_MAX_LEVELS];       /* power thresholds              papr.c:139,170 */
+    int64_t  level_count[PAPR_MAX_LEVELS]; /* samples with power > level[j] papr.c:147-151,179-183 */
+    /* diagnostics (not printed) */
+    int32_t  mode_used;                    /* PAPR_MODE_TWO_PASS or PAPR_MODE_FUSED */
+    int32_t  fused_miss;                   /* 1 if the fused pass missed and the exact pass re-ran */
+    float    device_ms;                    /* GPU time of the analysis (CUDA events on the engine stream) */
+    float    scan_ms;                      /* GPU time of the dominant scan kernel launch(es) */
+    uint32_t kernel_launches;              /* kernels launched for this analysis */
+    uint32_t reserved;
+    uint64_t h2d_bytes, d2h_bytes;         /* bytes moved across PCIe by this call */
+} papr_result;
+
+typedef struct papr_engine papr_engine;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  papr_abi_version(void);
+/* device < 0 : current device.  Allocates pinned staging and device work buffers lazily. */
+int  papr_engine_create(int device, papr_engine **out);
+void papr_engine_destroy(papr_engine *e);
+const char *papr_last_error(const papr_engine *e); /* e may be NULL: last create() error */
+/* cudaStream_t the engine launches on (for callers that time or order against it). */
+void *papr_engine_stream(papr_engine *e);
+/* Tunables by name ("mode", "presample_stride", "window_sigmas", "chunk_bytes", "staging_threads",
+ * "fused_min_samples", "fine_bytes_log2").  Returns PAPR_ERR_ARG for an unknown name. */
+int  papr_engine_set(papr_engine *e, const char *name, double value);
+
+/* ---- the process boundary: replaces main(), papr.c:32-196 ------------------------------------ */
+/* Same argv surface, same stdout/stderr text, returns the exit status instead of calling exit():
+ * 0 on success, 255 (the reference's exit(-1)) for usage / open errors, 1 for GPU failures.
+ * Extra knobs come from the environment only (PAPR_B200_DEVICES, PAPR_B200_MODE, ...), because
+ * any extra argv makes the reference print its usage text. */
+int papr_main(int argc, char **argv);
+
+/* ---- whole analysis: replaces papr.c:100-190 minus the printf calls --------------------------- */
+/* Host buffer holding the FILE IMAGE (any length; a trailing lone I is paired with the stale Q
+ * exactly as the reference's chunked fread does, papr.c:100-103).  Pinned or pageable; streamed to
+ * the GPU through double-buffered cudaMemcpyAsync with the statistics pass overlapped. */
+int papr_analyze_host(papr_engine *e, const void *file_image, uint64_t file_bytes, int graph,
+                      papr_result *out);
+/* Device-resident complete samples. */
+int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t nsamples, int graph,
+                        papr_result *out);
+/* Open + mmap + papr_analyze_host. */
+int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out);
+
+/* ---- the stages, for sharded (multi-GPU / multi-process) callers ------------------------------ */
+/* papr.c:100-129 over [first_index, first_index+nsamples) held at d_iq.  Synchronous. */
+int papr_stats_device(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index,
+                      papr_stats *out);
+/* Fold `next` (the range immediately after `acc`) into `acc`; first occurrence wins ties. */
+void papr_stats_merge(papr_stats *acc, const papr_stats *next);
+/* papr.c:131,134,136-141 / 164-173: avg, papr and the threshold table from merged stats, with the
+ * host libm exactly as the reference evaluates them.  Returns the number of levels. */
+int papr_levels(const papr_stats *st, int graph, double *avg, float *papr, float *level, int cap);
+/* papr.c:143-153 / 175-185: level_count[j] += #{samples of this range with power > level[j]}. */
+int papr_ccdf_device(papr_engine *e, const float *d_iq, uint64_t nsamples, const float *level,
+                     int nlevels, int64_t *level_count);
+/* Fused single-pass variant for a shard: phase 1 estimates (sum, sum of squares, blocks) of block
+ * sums from a strided subsample; the caller sums pre[4] over ranks; phase 2 scans the shard once;
+ * phase 3, given the merged stats of ALL ranks, produces this shard's counts or reports a miss
+ * (returns 1) in which case the caller falls back to papr_ccdf_device on every rank. */
+int papr_fused_presample(papr_engine *e, const float *d_iq, uint64_t nsamples, int graph, double pre[4]);
+int papr_fused_scan(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index,
+                    const double pre[4], int graph, papr_stats *out);
+int papr_fused_counts(papr_engine *e, const papr_stats *merged, int graph, int64_t *level_count);
+
+/* papr.c:132-135,154-161 / 186-190: the exact stdout text.  Returns its length, or <0. */
+long papr_format(const papr_result *r, char *out, size_t cap);
+/* Fill avg/papr/levels of `r` from r->stats (papr_levels) — for callers that merged shards. */
+int papr_result_finish(papr_result *r, int graph);
+
+/* ---- synthetic captures (SURVEY.md Appendix A generator, bit-identical to its C/numpy twins) -- */
+int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first_index, uint64_t nsamples,
+                       uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAPR_B200_H */

@@ -1,0 +1,211 @@
+"""GPU parity tests (run by the driver with -m gpu on a B200): the CUDA path, called through the
+C ABI (ctypes -> libpapr_b200.so) and through the drop-in CLI, against
+  * the committed golden stdout of the unmodified reference binary (tests/golden/), bit for bit;
+  * the oracle restatement on seeded inputs the oracle finishes in seconds;
+  * size-independent properties at BASELINE.json's full single-GPU size.
+Tolerance: NONE — integer counts, offsets and every printed character must be identical.  (The one
+floating-point accumulator, the double sum, is checked to 1e-12 relative where it is compared
+directly; see DESIGN.md "the sequential sum".)"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_binding
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _gold(name, graph):
+    return open(os.path.join(GOLD, name + (".g.out" if graph else ".out")), "rb").read()
+
+
+@pytest.fixture(scope="module")
+def eng(built):
+    e = built.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch
+
+
+def _dev(torch, f32):
+    return torch.from_numpy(np.ascontiguousarray(f32)).to("cuda:0")
+
+
+# ---- golden vectors of the reference binary --------------------------------------------------------
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_cli_stdout_equals_reference(built, name, graph, manifest, tmp_path):
+    img = fixtures.image(name)
+    if fixtures.md5(img) != manifest[name]["input_md5"]:
+        pytest.skip("fixture drift")
+    p = tmp_path / (name + ".cfile")
+    p.write_bytes(img)
+    r = subprocess.run([built.cli_path()] + (["-g"] if graph else []) + [str(p)], capture_output=True)
+    assert r.returncode == 0 and r.stderr == b""
+    assert r.stdout == _gold(name, graph)
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_host_buffer_path_equals_reference(built, eng, name, graph, manifest):
+    img = fixtures.image(name)
+    if fixtures.md5(img) != manifest[name]["input_md5"]:
+        pytest.skip("fixture drift")
+    for chunk in (64 << 20, 1 << 20):  # one chunk / many chunks (+ the staging ring wrapping around)
+        eng.set("chunk_bytes", chunk)
+        assert built.format_result(eng.analyze_host(img, graph=graph)) == _gold(name, graph)
+    eng.set("chunk_bytes", 64 << 20)
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["two_pass", "fused"])
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+@pytest.mark.parametrize("name", [n for n in fixtures.FIXTURES if not n.startswith("odd")])
+def test_device_path_equals_reference(built, eng, torch_cuda, name, graph, mode, manifest):
+    img = fixtures.image(name)
+    if fixtures.md5(img) != manifest[name]["input_md5"]:
+        pytest.skip("fixture drift")
+    f = np.frombuffer(img, np.float32)
+    d = _dev(torch_cuda, f) if f.size else torch_cuda.empty(4, device="cuda:0")
+    eng.set("mode", mode)
+    try:
+        res = eng.analyze_device(d, f.size // 2, graph)
+    finally:
+        eng.set("mode", 0)
+    assert built.format_result(res) == _gold(name, graph)
+    assert res.mode_used == mode
+
+
+def test_pinned_source_goes_direct(built, eng, torch_cuda):
+    f = torch_cuda.from_numpy(fixtures.siggen(0, 300_000, 11)).pin_memory()
+    res = eng.analyze_host(f, graph=True)
+    assert built.format_result(res) == oracle_binding.run_image(f.numpy().tobytes(), True)
+    assert res.h2d_bytes == 300_000 * 8
+
+
+# ---- seeded inputs against the oracle --------------------------------------------------------------
+def test_device_generator_equals_c_twin(eng, torch_cuda):
+    for first, n, seed in [(0, 100_003, 1), (2 ** 32 - 1000, 5000, 2), (2 ** 35 + 12345, 70_001, 3)]:
+        d = torch_cuda.empty(2 * n, dtype=torch_cuda.float32, device="cuda:0")
+        eng.siggen(d, first, n, seed)
+        assert np.array_equal(d.cpu().numpy(), oracle_binding.siggen(first, n, seed))
+
+
+@pytest.mark.parametrize("nsamples,seed", [(1 << 22, 1), ((1 << 24) + 12345, 2)])
+def test_seeded_against_oracle_all_modes(built, eng, torch_cuda, nsamples, seed):
+    d = torch_cuda.empty(2 * nsamples, dtype=torch_cuda.float32, device="cuda:0")
+    eng.siggen(d, 0, nsamples, seed)
+    host = d.cpu().numpy()
+    for graph in (False, True):
+        st, avg, papr, level, counts = oracle_binding.analyze(host, graph)
+        want = oracle_binding.run_image(host.tobytes(), graph)
+        for mode in (1, 2):
+            eng.set("mode", mode)
+            res = eng.analyze_device(d, nsamples, graph)
+            eng.set("mode", 0)
+            assert res.counts() == counts.tolist()  # (a fused miss at these small sizes re-runs exactly)
+            assert np.array_equal(np.array(res.levels(), np.float32), level)
+            assert abs(res.stats.sum - st.sum) <= 1e-12 * st.sum
+            assert built.format_result(res) == want
+        assert built.format_result(eng.analyze_host(host, graph=graph)) == want
+
+
+def test_virtual_shards_on_one_gpu(built, eng, torch_cuda):
+    """N byte-range shards through the stage API + host merge == the whole capture."""
+    f = np.frombuffer(fixtures.image("appA_1M"), np.float32)
+    d = _dev(torch_cuda, f)
+    n = f.size // 2
+    for graph in (False, True):
+        for nshard in (2, 3, 8):
+            cuts = [((n * k // nshard) + 1) & ~1 for k in range(nshard)] + [n]  # float4-aligned cuts
+            parts = [eng.stats_shard(d[2 * a:], b - a, a) for a, b in zip(cuts[:-1], cuts[1:])]
+            merged = built.merge_stats(parts)
+            _, _, lv = built.levels(merged, graph)
+            counts = np.zeros(len(lv), np.int64)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                counts += np.array(eng.ccdf_shard(d[2 * a:], b - a, lv), np.int64)
+            res = built.papr.result_from_parts(merged, graph, counts.tolist())
+            assert built.format_result(res) == _gold("appA_1M", graph)
+
+
+def test_fused_stage_api_and_forced_miss(built, eng, torch_cuda):
+    f = np.frombuffer(fixtures.image("gauss_1M"), np.float32)
+    d = _dev(torch_cuda, f)
+    n = f.size // 2
+    pre = eng.fused_presample(d, n, True)
+    assert pre[2] > 16
+    st = eng.fused_scan(d, n, 0, pre, True)
+    miss, cnt = eng.fused_counts(st, True)
+    res = built.papr.result_from_parts(st, True, [cnt[j] for j in range(2048)])
+    assert not miss and built.format_result(res) == _gold("gauss_1M", True)
+    # a wrong prediction (mean off by 3 %) must be detected, never silently accepted
+    bad = [pre[0] * 1.03, pre[1] * 1.03 ** 2, pre[2], 0.0]
+    st2 = eng.fused_scan(d, n, 0, bad, True)
+    assert st2.as_tuple() == st.as_tuple()
+    miss2, _ = eng.fused_counts(st2, True)
+    assert miss2
+
+
+def test_generic_bsearch_kernel(built, eng, torch_cuda):
+    """Force the fallback for plans whose fine table does not fit (PLAN_BSEARCH)."""
+    eng.set("fine_bytes_log2", 8)
+    try:
+        for name in ("burst", "appA_300k_s7", "denorm"):
+            f = np.frombuffer(fixtures.image(name), np.float32)
+            d = _dev(torch_cuda, f)
+            for graph in (False, True):
+                eng.set("mode", 1)
+                res = eng.analyze_device(d, f.size // 2, graph)
+                assert built.format_result(res) == _gold(name, graph)
+    finally:
+        eng.set("fine_bytes_log2", 26)
+        eng.set("mode", 0)
+
+
+def test_misaligned_pointer_is_rejected(built, eng, torch_cuda):
+    d = torch_cuda.zeros(1024, dtype=torch_cuda.float32, device="cuda:0")
+    with pytest.raises(built.PaprError):
+        eng.analyze_device(d[2:], 100, False)
+
+
+# ---- properties at BASELINE.json's single-GPU size --------------------------------------------------
+@pytest.mark.parametrize("log2n", [29])
+def test_full_size_properties(built, eng, torch_cuda, log2n):
+    """4 GiB (configs[1]): fused == two-pass; halves merge to the whole; counts are additive over
+    shards, monotone in the level and bounded by N; a prefix that the oracle can afford matches."""
+    n = 1 << log2n
+    d = torch_cuda.empty(2 * n, dtype=torch_cuda.float32, device="cuda:0")
+    eng.siggen(d, 0, n, 1)
+    out = {}
+    for graph in (False, True):
+        for mode in (1, 2):
+            eng.set("mode", mode)
+            out[graph, mode] = eng.analyze_device(d, n, graph)
+        eng.set("mode", 0)
+        a, b = out[graph, 1], out[graph, 2]
+        assert b.fused_miss == 0
+        assert a.stats.as_tuple() == b.stats.as_tuple() and a.counts() == b.counts()
+        assert built.format_result(a) == built.format_result(b)
+        c = a.counts()
+        assert all(x >= y for x, y in zip(c, c[1:])) and 0 < c[0] < n and c[-1] >= 1
+    res = out[False, 1]
+    h = n // 2
+    parts = [eng.stats_shard(d, h, 0), eng.stats_shard(d[2 * h:], n - h, h)]
+    m = built.merge_stats(parts)
+    assert m.as_tuple()[2:] == res.stats.as_tuple()[2:] and abs(m.sum - res.stats.sum) <= 1e-13 * m.sum
+    lv = res.levels()
+    c2 = np.array(eng.ccdf_shard(d, h, lv)) + np.array(eng.ccdf_shard(d[2 * h:], n - h, lv))
+    assert c2.tolist() == res.counts()
+    # Appendix-A known answer on the first 2^20 samples of the same stream (seed 1)
+    head = eng.analyze_device(d, 1 << 20, False)
+    assert built.format_result(head) == _gold("appA_1M", False)
