@@ -2,7 +2,7 @@
 //
 // HBM layout (per GPU):
 //   capture shard      float32 I/Q interleaved, exactly the file bytes (gr_complex, papr.c:101-103)
-//   warp partials      PaprWarpPartial[grid*32]   running pass-1 state of each resident warp
+//   CTA partials       PaprCtaPartial[grid]        running pass-1 state of each resident CTA
 //   cell histogram     u64[16384]                 samples per "cell" = float32 bit pattern >> sh
 //   ambiguity map      u32[16384]                 cell -> 1 + first fine-table counter, 0 = unambiguous
 //   fine table         u64[slots << sh]           one counter per float32 value of an ambiguous cell
@@ -11,9 +11,16 @@
 #include <stdint.h>
 #include "../../include/papr_b200.h"
 
+#ifndef PAPR_THREADS
 #define PAPR_THREADS 1024                      // threads per CTA of the scan kernels
+#endif
 #define PAPR_WARPS (PAPR_THREADS / 32)
+#ifndef PAPR_U
 #define PAPR_U 4                               // float4 loads in flight per lane per batch
+#endif
+#ifndef PAPR_CTAS_PER_SM
+#define PAPR_CTAS_PER_SM 1
+#endif
 #define PAPR_BATCH_VEC (32 * PAPR_U)           // float4 per warp batch
 #define PAPR_BATCH_SAMPLES (2 * PAPR_BATCH_VEC)// 256 samples = 2 KiB contiguous per warp batch
 #define PAPR_NCELLS_MAX 16384                  // cells of the shared-memory histogram
@@ -33,8 +40,9 @@ struct PaprDevStats {
     unsigned int flags;
 };
 
-// running pass-1 state of one warp, persistent across the chunk launches of a streamed shard
-struct PaprWarpPartial {
+// running pass-1 state of one CTA, persistent across the chunk launches of a streamed shard
+// (all-zero bytes = the reference's initial values, papr.c:37-49, so a memset resets it)
+struct PaprCtaPartial {
     double sum;
     unsigned long long idx[PAPR_NTRACK];
     int val[PAPR_NTRACK];
@@ -60,6 +68,8 @@ struct PaprDevLevels {
     double ratio;       // (double)peak / avg
     int L;
     int graph;
+    int status;         // RES_* bits set by the resolve kernel; cleared whenever the levels are (re)written
+    int pad;
     float level[PAPR_MAX_LEVELS];
 };
 
@@ -70,7 +80,7 @@ struct PaprScanArgs {
     const float *iq;               // 16-byte aligned
     unsigned long long nsamples;   // complete samples in this launch, < 2^32
     unsigned long long first_index;// global sample index of iq[0]
-    PaprWarpPartial *wp;           // [gridDim.x * PAPR_WARPS]
+    PaprCtaPartial *wp;            // [gridDim.x]
     const PaprPlan *plan;
     const unsigned *fine_base;     // [PAPR_NCELLS_MAX] 1 + first fine-table counter of the cell, 0 = none
     unsigned long long *g_hist;    // [PAPR_NCELLS_MAX]
@@ -86,21 +96,22 @@ struct PaprTables {
 };
 
 void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cudaStream_t s);
-void papr_launch_partials_reset(PaprWarpPartial *wp, int nwarps, cudaStream_t s);
-void papr_launch_stats_finalize(const PaprWarpPartial *wp, int nwarps, unsigned long long n,
-                                PaprDevStats *out, cudaStream_t s);
+void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprDevStats *out,
+                                cudaStream_t s);
+void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
+                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s);
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
                         PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s);
 void papr_launch_presample(const float *iq, unsigned long long nsamples, int stride, int grid,
-                           double *warp_pre /* [grid*PAPR_WARPS*3] */, cudaStream_t s);
-void papr_launch_presample_reduce(const double *warp_pre, int nwarps, double *pre4, cudaStream_t s);
-void papr_launch_plan_pred(const double *pre4, PaprTables t, int graph, float sigmas, int fine_slots,
-                           PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
+                           double *cta_pre /* [grid*3] */, cudaStream_t s);
+void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s);
+void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas,
+                           int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
 void papr_launch_plan_exact(const PaprDevLevels *lv, const PaprDevStats *merged, int fine_bytes_log2,
                             PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
 void papr_launch_zero_fine(const PaprPlan *plan, unsigned long long *g_fine, int grid, cudaStream_t s);
 void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
-                         unsigned long long *g_hist /* turned into suffix sums */,
+                         const unsigned long long *g_hist,
                          const unsigned long long *g_fine, const unsigned long long *g_over,
                          unsigned long long *counts, int *status, int grid, cudaStream_t s);
 void papr_launch_bsearch(const float *iq, unsigned long long nsamples, const PaprPlan *plan,

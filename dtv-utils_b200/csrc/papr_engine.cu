@@ -38,27 +38,28 @@ constexpr u64 kMaxLaunchSamples = 1ull << 31;  // per scan launch (32-bit sample
 constexpr int kLevels1dB = 256;            // table sizes: PAPR < 192.7 dB (papr_b200.h)
 constexpr int kLevelsGraph = PAPR_MAX_LEVELS;
 
-// everything one memset clears before an analysis
-struct Ctl {
+constexpr int kMaxGrid = 1024;
+
+// device scratch that ONE memset clears before an analysis (all-zero = the reference's initial state)
+struct DevWork {
     u64 hist[PAPR_NCELLS_MAX];
     u64 over;
-    u64 counts[PAPR_MAX_LEVELS + 1];
     u64 bhist[PAPR_MAX_LEVELS + 1];
-    u64 nan_idx;
-    int status;
-    int pad;
+    PaprCtaPartial wp[kMaxGrid];
 };
 
-// pinned mirror of the device results, filled by one batch of D2H copies
-struct HostOut {
-    PaprDevStats merged;
-    PaprDevStats local;
-    PaprDevLevels lv;
+// device results that ONE D2H copy fetches; HostOut (pinned) mirrors it
+struct DevOut {
+    PaprDevStats local;   // this shard
+    PaprDevStats merged;  // all shards (single-shard analysis: == local)
     PaprPlan plan;
     u64 counts[PAPR_MAX_LEVELS + 1];
+    PaprDevLevels lv;
+};
+
+struct HostOut {
+    DevOut o;
     u64 nan_idx;
-    int status;
-    int pad;
     float nan_sample[2];
     double pre4[4];
 };
@@ -131,7 +132,7 @@ struct papr_engine {
     std::string err;
     // tunables
     int mode = PAPR_MODE_AUTO;
-    int presample_stride = 32;
+    int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
     size_t chunk_bytes = 64u << 20;
     int staging_threads = 8;
@@ -139,15 +140,13 @@ struct papr_engine {
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
     // device work buffers
-    int grid = 0, nwarps = 0;
-    PaprWarpPartial *d_wp = nullptr;
-    Ctl *d_ctl = nullptr;
+    int grid = 0;
+    DevWork *d_work = nullptr;
+    DevOut *d_out = nullptr;
+    u64 *d_nan_idx = nullptr;
     unsigned *d_fine_base = nullptr;
     u64 *d_fine = nullptr;
-    PaprPlan *d_plan = nullptr;
-    PaprDevStats *d_stats = nullptr; // [0] local, [1] merged
-    PaprDevLevels *d_levels = nullptr;
-    double *d_pre_wp = nullptr, *d_pre4 = nullptr;
+    double *d_pre_cta = nullptr, *d_pre4 = nullptr;
     double *d_tables = nullptr; // pow10[2][MAX] | ratio_min[2][MAX]
     HostOut *h_out = nullptr;
     // host path
@@ -215,15 +214,14 @@ static int engine_init(papr_engine *e, int device)
     CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     if (papr_scan_configure() != 0) return fail(e, PAPR_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed");
     e->grid = e->num_sms * e->grid_per_sm;
-    e->nwarps = e->grid * PAPR_WARPS;
-    CU(cudaMalloc(&e->d_wp, sizeof(PaprWarpPartial) * e->nwarps));
-    CU(cudaMalloc(&e->d_ctl, sizeof(Ctl)));
+    if (e->grid > kMaxGrid) return fail(e, PAPR_ERR_CUDA, "more SMs than this build supports");
+    CU(cudaMalloc(&e->d_work, sizeof(DevWork)));
+    CU(cudaMalloc(&e->d_out, sizeof(DevOut)));
+    CU(cudaMemset(e->d_out, 0, sizeof(DevOut)));
+    CU(cudaMalloc(&e->d_nan_idx, sizeof(u64)));
     CU(cudaMalloc(&e->d_fine_base, sizeof(unsigned) * PAPR_NCELLS_MAX));
     CU(cudaMalloc(&e->d_fine, (size_t)1 << e->fine_bytes_log2));
-    CU(cudaMalloc(&e->d_plan, sizeof(PaprPlan)));
-    CU(cudaMalloc(&e->d_stats, 2 * sizeof(PaprDevStats)));
-    CU(cudaMalloc(&e->d_levels, sizeof(PaprDevLevels)));
-    CU(cudaMalloc(&e->d_pre_wp, sizeof(double) * 3 * e->nwarps));
+    CU(cudaMalloc(&e->d_pre_cta, sizeof(double) * 3 * e->grid));
     CU(cudaMalloc(&e->d_pre4, sizeof(double) * 4));
     CU(cudaMalloc(&e->d_tables, sizeof(double) * 4 * PAPR_MAX_LEVELS));
     CU(cudaHostAlloc(&e->h_out, sizeof(HostOut), cudaHostAllocDefault));
@@ -261,8 +259,8 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (!e) return;
     delete e->pool;
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_wp); cudaFree(e->d_ctl); cudaFree(e->d_fine_base); cudaFree(e->d_fine);
-    cudaFree(e->d_plan); cudaFree(e->d_stats); cudaFree(e->d_levels); cudaFree(e->d_pre_wp);
+    cudaFree(e->d_work); cudaFree(e->d_out); cudaFree(e->d_nan_idx); cudaFree(e->d_fine_base); cudaFree(e->d_fine);
+    cudaFree(e->d_pre_cta);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
     if (e->h_out) cudaFreeHost(e->h_out);
     for (auto &p : e->h_stage) if (p) cudaFreeHost(p);
@@ -297,10 +295,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
 // ------------------------------------------------------------------------------------------------
 static int enqueue_reset(papr_engine *e)
 {
-    papr_launch_partials_reset(e->d_wp, e->nwarps, e->stream);
-    CU(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
-    CU(cudaMemsetAsync(&e->d_ctl->nan_idx, 0xff, sizeof(u64), e->stream));
-    e->launches += 1;
+    CU(cudaMemsetAsync(e->d_work, 0, sizeof(DevWork), e->stream));
     return PAPR_OK;
 }
 
@@ -309,12 +304,12 @@ static void scan_args(papr_engine *e, PaprScanArgs &a, const float *d_iq, u64 n,
     a.iq = d_iq;
     a.nsamples = n;
     a.first_index = first;
-    a.wp = e->d_wp;
-    a.plan = e->d_plan;
+    a.wp = e->d_work->wp;
+    a.plan = &e->d_out->plan;
     a.fine_base = e->d_fine_base;
-    a.g_hist = e->d_ctl->hist;
+    a.g_hist = e->d_work->hist;
     a.g_fine = e->d_fine;
-    a.g_over = &e->d_ctl->over;
+    a.g_over = &e->d_work->over;
 }
 
 // one pass over [d_iq, d_iq + 2n) split into launches of < 2^32 samples at batch-aligned cuts
@@ -337,38 +332,39 @@ static int enqueue_scan(papr_engine *e, bool stats, bool hist, const float *d_iq
     return PAPR_OK;
 }
 
-// warp partials -> local stats -> (single shard) merged stats, avg, L, levels on the device
+// CTA partials -> local stats -> (single shard) merged stats, avg, L, levels on the device
 static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph)
 {
-    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
-    papr_launch_levels(&e->d_stats[0], 1, e->tables(graph), graph, &e->d_stats[1], e->d_levels, e->stream);
-    e->launches += 2;
+    papr_launch_finalize_levels(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
+                                &e->d_out->lv, e->stream);
+    e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
 }
 
 static int enqueue_resolve(papr_engine *e)
 {
-    papr_launch_resolve(e->d_plan, e->d_fine_base, e->d_levels, e->d_ctl->hist, e->d_fine, &e->d_ctl->over,
-                        e->d_ctl->counts, &e->d_ctl->status, e->num_sms * 2, e->stream);
-    e->launches += 2;
+    papr_launch_resolve(&e->d_out->plan, e->d_fine_base, &e->d_out->lv, e->d_work->hist, e->d_fine, &e->d_work->over,
+                        e->d_out->counts, &e->d_out->lv.status, e->num_sms * 2, e->stream);
+    e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
 }
 
-// exact-threshold CCDF pass over resident data (d_levels / d_stats[1] already hold levels and peak)
+// exact-threshold CCDF pass over resident data (d_out->lv / d_out->merged already hold levels and peak)
 static int enqueue_hist_exact(papr_engine *e, const float *d_iq, u64 n, bool timed)
 {
-    papr_launch_plan_exact(e->d_levels, &e->d_stats[1], e->fine_bytes_log2, e->d_plan, e->d_fine_base, e->stream);
-    papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
+    papr_launch_plan_exact(&e->d_out->lv, &e->d_out->merged, e->fine_bytes_log2, &e->d_out->plan, e->d_fine_base,
+                           e->stream);
+    papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 2;
     int rc = enqueue_scan(e, false, true, d_iq, n, 0, timed);
     if (rc) return rc;
-    papr_launch_bsearch(d_iq, n, e->d_plan, e->d_levels, e->d_ctl->bhist, e->grid, e->stream); // no-op unless PLAN_BSEARCH
+    papr_launch_bsearch(d_iq, n, &e->d_out->plan, &e->d_out->lv, e->d_work->bhist, e->grid, e->stream); // no-op unless PLAN_BSEARCH
     e->launches += 1;
     rc = enqueue_resolve(e);
     if (rc) return rc;
-    papr_launch_bsearch_counts(e->d_plan, e->d_levels, e->d_ctl->bhist, e->d_ctl->counts, e->stream);
+    papr_launch_bsearch_counts(&e->d_out->plan, &e->d_out->lv, e->d_work->bhist, e->d_out->counts, e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
@@ -376,14 +372,8 @@ static int enqueue_hist_exact(papr_engine *e, const float *d_iq, u64 n, bool tim
 
 static int enqueue_fetch(papr_engine *e)
 {
-    HostOut *h = e->h_out;
-    CU(cudaMemcpyAsync(&h->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&h->merged, &e->d_stats[1], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&h->lv, e->d_levels, sizeof(PaprDevLevels), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&h->plan, e->d_plan, sizeof(PaprPlan), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(h->counts, e->d_ctl->counts, sizeof(h->counts), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&h->status, &e->d_ctl->status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    e->d2h += 2 * sizeof(PaprDevStats) + sizeof(PaprDevLevels) + sizeof(PaprPlan) + sizeof(h->counts) + sizeof(int);
+    CU(cudaMemcpyAsync(&e->h_out->o, e->d_out, sizeof(DevOut), cudaMemcpyDeviceToHost, e->stream));
+    e->d2h += sizeof(DevOut);
     return PAPR_OK;
 }
 
@@ -452,8 +442,9 @@ static void begin_analysis(papr_engine *e)
 static int fix_nan_sign(papr_engine *e, const float *d_iq, u64 n, u64 first, papr_stats *st)
 {
     if (!std::isnan(st->sum) || n == 0) return PAPR_OK;
-    papr_launch_find_nan(d_iq, n, first, &e->d_ctl->nan_idx, e->num_sms * 8, e->stream);
-    CU(cudaMemcpyAsync(&e->h_out->nan_idx, &e->d_ctl->nan_idx, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemsetAsync(e->d_nan_idx, 0xff, sizeof(u64), e->stream));
+    papr_launch_find_nan(d_iq, n, first, e->d_nan_idx, e->num_sms * 8, e->stream);
+    CU(cudaMemcpyAsync(&e->h_out->nan_idx, e->d_nan_idx, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     u64 k = e->h_out->nan_idx;
     if (k == ~0ull) return PAPR_OK; // Inf - Inf cannot occur (powers are >= 0); nothing to do
@@ -471,13 +462,13 @@ static int fix_nan_sign(papr_engine *e, const float *d_iq, u64 n, u64 first, pap
 // (or the fused pass missed): the caller must run the exact CCDF pass with out->level[].
 static int collect(papr_engine *e, int graph, papr_result *out, bool counts_valid)
 {
-    const HostOut *h = e->h_out;
+    const DevOut *h = &e->h_out->o;
     papr_result_finish(out, graph);
     int redo = 0;
     if (out->nlevels > 0) {
         bool same = h->lv.L == out->nlevels &&
                     memcmp(h->lv.level, out->level, sizeof(float) * (size_t)out->nlevels) == 0;
-        if (!same || !counts_valid || (h->status & RES_MISS)) redo = 1;
+        if (!same || !counts_valid || (h->lv.status & RES_MISS)) redo = 1;
         if (!redo)
             for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)h->counts[j];
     }
@@ -490,12 +481,12 @@ static int upload_levels(papr_engine *e, const float *level, int L, float peak)
     static thread_local PaprDevStats ms;
     memset(&ms, 0, sizeof(ms));
     memcpy(&ms.val[TR_PEAK], &peak, 4);
-    lv.avg = 0; lv.ratio = 0; lv.L = L; lv.graph = 0;
+    lv.avg = 0; lv.ratio = 0; lv.L = L; lv.graph = 0; lv.status = 0; lv.pad = 0;
     memcpy(lv.level, level, sizeof(float) * (size_t)L);
     // pageable -> the runtime stages these synchronously, so the thread_local sources may be reused
-    CU(cudaMemcpyAsync(e->d_levels, &lv, offsetof(PaprDevLevels, level) + sizeof(float) * (size_t)L,
+    CU(cudaMemcpyAsync(&e->d_out->lv, &lv, offsetof(PaprDevLevels, level) + sizeof(float) * (size_t)L,
                        cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(&e->d_stats[1], &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(&e->d_out->merged, &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
     e->h2d += sizeof(float) * (size_t)L + sizeof(ms);
     return PAPR_OK;
 }
@@ -506,18 +497,16 @@ static int run_exact_ccdf(papr_engine *e, const float *d_iq, u64 n, const float 
 {
     int rc = upload_levels(e, level, L, peak);
     if (rc) return rc;
-    CU(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
+    if ((rc = enqueue_reset(e))) return rc;
     rc = enqueue_hist_exact(e, d_iq, n, true);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(e->h_out->counts, e->d_ctl->counts, sizeof(u64) * (size_t)L, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&e->h_out->status, &e->d_ctl->status, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(&e->h_out->plan, e->d_plan, sizeof(PaprPlan), cudaMemcpyDeviceToHost, e->stream));
+    if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaStreamSynchronize(e->stream));
-    e->d2h += sizeof(u64) * (size_t)L + sizeof(int);
-    if (e->h_out->status & RES_MISS) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+    const DevOut *h = &e->h_out->o;
+    if (h->lv.status & RES_MISS) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
     for (int j = 0; j < L; ++j) {
-        if (accumulate) level_count[j] += (int64_t)e->h_out->counts[j];
-        else level_count[j] = (int64_t)e->h_out->counts[j];
+        if (accumulate) level_count[j] += (int64_t)h->counts[j];
+        else level_count[j] = (int64_t)h->counts[j];
     }
     return PAPR_OK;
 }
@@ -554,12 +543,11 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if ((rc = enqueue_reset(e))) return rc;
     if (mode == PAPR_MODE_FUSED) {
         papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES), stride,
-                              e->grid, e->d_pre_wp, e->stream);
-        papr_launch_presample_reduce(e->d_pre_wp, e->nwarps, e->d_pre4, e->stream);
-        papr_launch_plan_pred(e->d_pre4, e->tables(graph), graph, e->window_sigmas,
-                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), e->d_plan, e->d_fine_base, e->stream);
-        papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
-        e->launches += 4;
+                              e->grid, e->d_pre_cta, e->stream);
+        papr_launch_plan_pred(nullptr, e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas,
+                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
+        papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
+        e->launches += 3;
         if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
         if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
         if ((rc = enqueue_resolve(e))) return rc;
@@ -571,7 +559,7 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    stats_to_host(e->h_out->merged, &out->stats);
+    stats_to_host(e->h_out->o.merged, &out->stats);
     if ((rc = fix_nan_sign(e, d_iq, n, 0, &out->stats))) return rc;
     if (collect(e, graph, out, true)) {
         out->fused_miss = mode == PAPR_MODE_FUSED;
@@ -595,11 +583,11 @@ extern "C" int papr_stats_device(papr_engine *e, const float *d_iq, uint64_t n, 
     int rc;
     if ((rc = enqueue_reset(e))) return rc;
     if ((rc = enqueue_scan(e, true, false, d_iq, n, first, true))) return rc;
-    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
     e->launches += 1;
-    CU(cudaMemcpyAsync(&e->h_out->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    stats_to_host(e->h_out->local, out);
+    stats_to_host(e->h_out->o.local, out);
     return fix_nan_sign(e, d_iq, n, first, out);
 }
 
@@ -621,8 +609,8 @@ extern "C" int papr_fused_presample(papr_engine *e, const float *d_iq, uint64_t 
     if (!e || !pre || (n && !d_iq)) return PAPR_ERR_ARG;
     begin_analysis(e);
     papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
-                          presample_stride_for(e, n, graph ? 1 : 0), e->grid, e->d_pre_wp, e->stream);
-    papr_launch_presample_reduce(e->d_pre_wp, e->nwarps, e->d_pre4, e->stream);
+                          presample_stride_for(e, n, graph ? 1 : 0), e->grid, e->d_pre_cta, e->stream);
+    papr_launch_presample_reduce(e->d_pre_cta, e->grid, e->d_pre4, e->stream);
     CU(cudaMemcpyAsync(e->h_out->pre4, e->d_pre4, sizeof(double) * 4, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     memcpy(pre, e->h_out->pre4, sizeof(double) * 4);
@@ -640,16 +628,16 @@ extern "C" int papr_fused_scan(papr_engine *e, const float *d_iq, uint64_t n, ui
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
     CU(cudaMemcpyAsync(e->d_pre4, pre, sizeof(double) * 4, cudaMemcpyHostToDevice, e->stream));
-    papr_launch_plan_pred(e->d_pre4, e->tables(graph), graph, e->window_sigmas,
-                          1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), e->d_plan, e->d_fine_base, e->stream);
-    papr_launch_zero_fine(e->d_plan, e->d_fine, e->num_sms * 4, e->stream);
+    papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas,
+                          1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
+    papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 2;
     if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
-    papr_launch_stats_finalize(e->d_wp, e->nwarps, n, &e->d_stats[0], e->stream);
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
     e->launches += 1;
-    CU(cudaMemcpyAsync(&e->h_out->local, &e->d_stats[0], sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    stats_to_host(e->h_out->local, out);
+    stats_to_host(e->h_out->o.local, out);
     return fix_nan_sign(e, d_iq, n, first, out);
 }
 
@@ -663,8 +651,8 @@ extern "C" int papr_fused_counts(papr_engine *e, const papr_stats *merged, int g
     if (r.nlevels == 0) return PAPR_OK;
     PaprDevStats ms;
     stats_to_device(*merged, &ms);
-    CU(cudaMemcpyAsync(&e->d_stats[0], &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
-    papr_launch_levels(&e->d_stats[0], 1, e->tables(graph), graph, &e->d_stats[1], e->d_levels, e->stream);
+    CU(cudaMemcpyAsync(&e->d_out->local, &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
+    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv, e->stream);
     e->launches += 1;
     int rc;
     if ((rc = enqueue_resolve(e))) return rc;
@@ -712,17 +700,15 @@ static int ensure_staging(papr_engine *e)
     return PAPR_OK;
 }
 
-extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t bytes, int graph, papr_result *out)
+// Stream the file image into the resident device buffer, running the statistics pass on each chunk
+// as it lands.  On return everything is enqueued; *n_out = samples (incl. the lone-I tail sample).
+static int host_stream_stats(papr_engine *e, const void *image, uint64_t bytes, u64 first, u64 *n_out)
 {
-    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
-    graph = graph ? 1 : 0;
-    begin_analysis(e);
-    memset(out, 0, offsetof(papr_result, level));
-    out->mode_used = PAPR_MODE_TWO_PASS;
     const unsigned char *img = (const unsigned char *)image;
     const u64 nfloats = bytes / 4, npairs = nfloats / 2;
     const bool tail = (nfloats & 1) != 0;
     const u64 n = npairs + (tail ? 1 : 0); // papr.c:102: a lone trailing I still counts as a sample
+    *n_out = n;
     int rc;
     if ((rc = ensure_device_buffer(e, n * 8 + 16))) return rc;
 
@@ -731,7 +717,6 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
     cudaGetLastError();
     if (!pinned && npairs && (rc = ensure_staging(e))) return rc;
 
-    CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
     float tail_pair[2] = {0.f, 0.f};
     if (tail) {
@@ -740,8 +725,8 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
     }
     const u64 chunk_samples = e->chunk_bytes / 8;
     int stage = 0;
-    for (u64 off = 0; off < n || off == 0; off += chunk_samples) {
-        const u64 m = std::min(chunk_samples, n - off);        // samples of this chunk (incl. the tail sample)
+    for (u64 off = 0; off < n; off += chunk_samples) {
+        const u64 m = std::min(chunk_samples, n - off);              // samples of this chunk (incl. the tail sample)
         const u64 mp = std::min(m, npairs > off ? npairs - off : 0); // complete pairs to copy from the image
         if (mp) {
             const void *src = img + off * 8;
@@ -763,15 +748,28 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
         }
         CU(cudaEventRecord(e->chunk_ready, e->copy_stream));
         CU(cudaStreamWaitEvent(e->stream, e->chunk_ready, 0));
-        if (m && (rc = enqueue_scan(e, true, false, e->d_buf + 2 * off, m, off, false))) return rc;
-        if (n == 0) break;
+        if ((rc = enqueue_scan(e, true, false, e->d_buf + 2 * off, m, first + off, false))) return rc;
     }
+    return PAPR_OK;
+}
+
+extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t bytes, int graph, papr_result *out)
+{
+    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    memset(out, 0, offsetof(papr_result, level));
+    out->mode_used = PAPR_MODE_TWO_PASS;
+    int rc;
+    u64 n = 0;
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    if ((rc = host_stream_stats(e, image, bytes, 0, &n))) return rc;
     if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
     if ((rc = enqueue_hist_exact(e, e->d_buf, n, true))) return rc;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    stats_to_host(e->h_out->merged, &out->stats);
+    stats_to_host(e->h_out->o.merged, &out->stats);
     if ((rc = fix_nan_sign(e, e->d_buf, n, 0, &out->stats))) return rc;
     if (collect(e, graph, out, true)) {
         rc = run_exact_ccdf(e, e->d_buf, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
@@ -781,6 +779,26 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
     }
     finish_timing(e, out);
     return PAPR_OK;
+}
+
+// Sharded callers with host-resident shards: pass 1 while streaming in; the shard stays resident at
+// *d_iq_out (engine-owned, valid until the next host-path call) for papr_ccdf_device.
+extern "C" int papr_stats_host(papr_engine *e, const void *image, uint64_t bytes, uint64_t first, papr_stats *out,
+                               const float **d_iq_out, uint64_t *nsamples_out)
+{
+    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    begin_analysis(e);
+    int rc;
+    u64 n = 0;
+    if ((rc = host_stream_stats(e, image, bytes, first, &n))) return rc;
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
+    e->launches += 1;
+    CU(cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->o.local, out);
+    if (d_iq_out) *d_iq_out = e->d_buf;
+    if (nsamples_out) *nsamples_out = n;
+    return fix_nan_sign(e, e->d_buf, n, first, out);
 }
 
 extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)

@@ -74,10 +74,10 @@ __device__ __forceinline__ bool better(int va, u64 ia, int vb, u64 ib)
 // ------------------------------------------------------------------------------------------------
 // the scan kernel: pass 1 (STATS), pass 2 (HIST) or both in one sweep over the shard
 // ------------------------------------------------------------------------------------------------
-// dynamic shared memory of the scan kernel: u32 hist[NCELLS_MAX+1] | u32 fine_base[NCELLS_MAX+1]
-// (cell NCELLS_MAX is the overflow cell: samples above the planned range)
+// dynamic shared memory of the scan kernel: u32 hist[NCELLS_MAX+2] | u32 fine_base[NCELLS_MAX+2]
+// slot 0 = below the planned range, slots 1..ncells = cells, slot ncells+1 = above the range
 extern __shared__ __align__(16) unsigned char scan_smem[];
-#define SCAN_SMEM_BYTES (8 * (PAPR_NCELLS_MAX + 1))
+#define SCAN_SMEM_BYTES (8 * (PAPR_NCELLS_MAX + 2))
 
 template <bool STATS, bool HIST>
 struct ScanState {
@@ -88,30 +88,43 @@ struct ScanState {
     unsigned upd;
     // pass 2
     u64 *g_fine;
-    unsigned smem_hist; // shared-window byte address of hist[0]
+    unsigned smem_slot1; // shared-window byte address of slot 1 (= cell 0)
     int sh, cell_base, ncells;
     unsigned fmask;
 };
 
-// One sample of the CCDF pass.  Branch-free up to the (warp-level infrequent) fine-table update:
-// cell index clamped into the overflow cell, predicated shared-memory reduction + lookup of the
-// cell's fine-table base (0 = no threshold can lie in this cell).
+// The CCDF pass, per sample.  No divergence up to the (warp-level infrequent) fine-table update:
+// the cell index is clamped into [0, ncells+1] where slot 0 collects everything below the planned
+// range (63 % of a Gaussian-like capture) and slot ncells+1 everything above it; every lane issues the
+// shared-memory increment (ATOMS.POPC.INC merges lanes that hit the same word, so the crowded slot 0
+// costs one update per warp) and reads the slot's fine-table base (0 = no threshold can lie here).
 template <bool STATS, bool HIST>
-__device__ __forceinline__ void hist_one(ScanState<STATS, HIST> &st, float v)
+__device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, unsigned bits)
 {
-    const unsigned bits = __float_as_uint(v);
-    const int d = min((int)(bits >> st.sh) - st.cell_base, st.ncells);
-    const unsigned addr = st.smem_hist + ((unsigned)d << 2);
-    unsigned fb = 0;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ge.s32 p, %1, 0;\n\t"
-        "@p red.shared.add.u32 [%2], 1;\n\t"
-        "@p ld.shared.u32 %0, [%2+%3];\n\t}"
-        : "+r"(fb)
-        : "r"(d), "r"(addr), "n"(4 * (PAPR_NCELLS_MAX + 1))
-        : "memory");
-    if (fb) atomicAdd(&st.g_fine[fb - 1u + (bits & st.fmask)], 1ull);
+    // shared-window byte address of the sample's slot
+    const int d = max(min((int)(bits >> st.sh) - st.cell_base, st.ncells), -1);
+    return st.smem_slot1 + ((unsigned)d << 2);
+}
+
+__device__ __forceinline__ unsigned hist_bump(unsigned addr)
+{
+    unsigned fb;
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(fb) : "r"(addr), "n"(4 * (PAPR_NCELLS_MAX + 2)));
+    return fb;
+}
+
+// the two samples of one 16-byte load
+template <bool STATS, bool HIST>
+__device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, float v1)
+{
+    const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
+    const unsigned f0 = hist_bump(hist_slot(st, b0));
+    const unsigned f1 = hist_bump(hist_slot(st, b1));
+    if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
+        if (f0) atomicAdd(&st.g_fine[f0 - 1u + (b0 & st.fmask)], 1ull);
+        if (f1) atomicAdd(&st.g_fine[f1 - 1u + (b1 & st.fmask)], 1ull);
+    }
 }
 
 template <int T, bool STATS, bool HIST>
@@ -138,7 +151,7 @@ __device__ __forceinline__ void track_update(ScanState<STATS, HIST> &st, const f
 
 template <bool STATS, bool HIST>
 __device__ __forceinline__ void process_batch(ScanState<STATS, HIST> &st, const float4 (&r)[PAPR_U],
-                                              unsigned batch_off, int lane, bool do_hist)
+                                              unsigned batch_off, int lane)
 {
     float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
 #pragma unroll
@@ -156,22 +169,25 @@ __device__ __forceinline__ void process_batch(ScanState<STATS, HIST> &st, const 
             bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
             bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
         }
-        if (HIST && do_hist) {
-            hist_one(st, v0);
-            hist_one(st, v1);
-        }
+        if (HIST) hist_pair(st, v0, v1);
     }
     if (STATS) {
-        track_update<TR_PEAK>(st, r, bm0, batch_off, lane);
-        track_update<TR_RE_POS>(st, r, bm1, batch_off, lane);
-        track_update<TR_RE_NEG>(st, r, bm2, batch_off, lane);
-        track_update<TR_IM_POS>(st, r, bm3, batch_off, lane);
-        track_update<TR_IM_NEG>(st, r, bm4, batch_off, lane);
+        // warp-uniform and rare after the first few batches: does any lane beat a running maximum?
+        const bool cand = __float_as_int(bm0) > st.run_val[TR_PEAK] || __float_as_int(bm1) > st.run_val[TR_RE_POS] ||
+                          __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
+                          __float_as_int(bm4) > st.run_val[TR_IM_NEG];
+        if (__any_sync(FULL, cand)) {
+            track_update<TR_PEAK>(st, r, bm0, batch_off, lane);
+            track_update<TR_RE_POS>(st, r, bm1, batch_off, lane);
+            track_update<TR_RE_NEG>(st, r, bm2, batch_off, lane);
+            track_update<TR_IM_POS>(st, r, bm3, batch_off, lane);
+            track_update<TR_IM_NEG>(st, r, bm4, batch_off, lane);
+        }
     }
 }
 
 template <bool STATS, bool HIST>
-__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprScanArgs a)
+__global__ void __launch_bounds__(PAPR_THREADS, PAPR_CTAS_PER_SM) papr_scan_kernel(const PaprScanArgs a)
 {
     ScanState<STATS, HIST> st;
     unsigned *s_hist = reinterpret_cast<unsigned *>(scan_smem);
@@ -184,20 +200,19 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprSc
         const PaprPlan pl = *a.plan;
         do_hist = (pl.status & PLAN_HIST) != 0;
         if (!STATS && !do_hist) return;
-        unsigned *s_fb = s_hist + (PAPR_NCELLS_MAX + 1);
+        unsigned *s_fb = s_hist + (PAPR_NCELLS_MAX + 2);
         st.g_fine = a.g_fine;
         // opaque to the optimiser on purpose: otherwise the window base is rematerialised per sample
         asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
-                     : "=r"(st.smem_hist) : "l"(s_hist));
+                     : "=r"(st.smem_slot1) : "l"(s_hist + 1));
         st.sh = pl.sh;
-        st.cell_base = pl.cell_base;
+        // without a valid plan (fused mode, nothing to predict from) every sample lands in slot 0
+        st.cell_base = do_hist ? pl.cell_base : 0x7fffffff;
         st.ncells = do_hist ? pl.ncells : 0;
         st.fmask = (1u << pl.sh) - 1u;
-        if (do_hist) {
-            for (int i = threadIdx.x; i <= st.ncells; i += PAPR_THREADS) {
-                s_hist[i] = 0;
-                s_fb[i] = i < st.ncells ? a.fine_base[i] : 0u;
-            }
+        for (int i = threadIdx.x; i < st.ncells + 2; i += PAPR_THREADS) {
+            s_hist[i] = 0;
+            s_fb[i] = (i >= 1 && i <= st.ncells) ? a.fine_base[i - 1] : 0u;
         }
         __syncthreads();
     }
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprSc
         st.upd = 0;
 #pragma unroll
         for (int t = 0; t < PAPR_NTRACK; ++t) {
-            st.run_val[t] = a.wp[gw].val[t]; // carried across the chunk launches of a streamed shard
+            st.run_val[t] = a.wp[blockIdx.x].val[t]; // carried across the chunk launches of a streamed shard
             st.run_pos[t] = 0;
         }
     }
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprSc
         float4 r[PAPR_U];
 #pragma unroll
         for (int u = 0; u < PAPR_U; ++u) r[u] = ldg_stream(q + 32 * u);
-        process_batch(st, r, b * PAPR_BATCH_SAMPLES, lane, do_hist);
+        process_batch(st, r, b * PAPR_BATCH_SAMPLES, lane);
     }
     // ragged last batch (zero padded: zeros add +0.0 to the sum, beat no maximum, exceed no threshold)
     const u64 done = (u64)nbatch_full * PAPR_BATCH_SAMPLES;
@@ -236,29 +251,52 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_kernel(const PaprSc
                 r[u].y = t.y;
             }
         }
-        process_batch(st, r, (unsigned)done, lane, do_hist);
+        process_batch(st, r, (unsigned)done, lane);
     }
 
     if (STATS) {
+        // CTA-level fold of the warps' states (fixed order), then into the CTA's persistent partial
+        __shared__ double s_wsum[PAPR_WARPS];
+        __shared__ int s_wval[PAPR_NTRACK][PAPR_WARPS];
+        __shared__ unsigned s_wpos[PAPR_NTRACK][PAPR_WARPS];
+        const int warp = threadIdx.x >> 5;
         double wsum = warp_sum_fixed(st.dsum);
         if (lane == 0) {
-            PaprWarpPartial *w = a.wp + gw;
-            w->sum += wsum;
+            s_wsum[warp] = wsum;
 #pragma unroll
-            for (int t = 0; t < PAPR_NTRACK; ++t)
-                if (st.upd & (1u << t)) {
-                    w->val[t] = st.run_val[t];
-                    w->idx[t] = a.first_index + st.run_pos[t];
+            for (int t = 0; t < PAPR_NTRACK; ++t) {
+                const bool u = (st.upd >> t) & 1u;
+                s_wval[t][warp] = u ? st.run_val[t] : 0; // 0 = nothing new from this warp
+                s_wpos[t][warp] = u ? st.run_pos[t] : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double x = lane < PAPR_WARPS ? s_wsum[lane] : 0.0;
+            x = warp_sum_fixed(x);
+            PaprCtaPartial *w = a.wp + blockIdx.x;
+            if (lane == 0) w->sum += x;
+#pragma unroll
+            for (int t = 0; t < PAPR_NTRACK; ++t) {
+                int v = lane < PAPR_WARPS ? s_wval[t][lane] : 0;
+                unsigned pos = lane < PAPR_WARPS ? s_wpos[t][lane] : 0xffffffffu;
+                const int vmax = __reduce_max_sync(FULL, v);
+                const unsigned pmin = __reduce_min_sync(FULL, v == vmax ? pos : 0xffffffffu);
+                // strictly greater than what earlier launches (= lower indices) left: first occurrence kept
+                if (lane == 0 && vmax > w->val[t]) {
+                    w->val[t] = vmax;
+                    w->idx[t] = a.first_index + pmin;
                 }
+            }
         }
     }
     if (HIST && do_hist) {
         __syncthreads();
         for (int i = threadIdx.x; i < st.ncells; i += PAPR_THREADS) {
-            unsigned c = s_hist[i];
+            unsigned c = s_hist[i + 1];
             if (c) atomicAdd(&a.g_hist[i], (u64)c);
         }
-        if (threadIdx.x == 0 && s_hist[st.ncells]) atomicAdd(a.g_over, (u64)s_hist[st.ncells]);
+        if (threadIdx.x == 0 && s_hist[st.ncells + 1]) atomicAdd(a.g_over, (u64)s_hist[st.ncells + 1]);
     }
 }
 
@@ -287,27 +325,10 @@ void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cu
 // ------------------------------------------------------------------------------------------------
 // pass-1 follow-ups
 // ------------------------------------------------------------------------------------------------
-__global__ void papr_partials_reset_kernel(PaprWarpPartial *wp, int nwarps)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nwarps) {
-        PaprWarpPartial z;
-        z.sum = 0.0;
-        z.pad = 0;
-        for (int t = 0; t < PAPR_NTRACK; ++t) { z.idx[t] = 0; z.val[t] = 0; } // papr.c:37-49 zero init
-        wp[i] = z;
-    }
-}
-
-void papr_launch_partials_reset(PaprWarpPartial *wp, int nwarps, cudaStream_t s)
-{
-    papr_partials_reset_kernel<<<(nwarps + 255) / 256, 256, 0, s>>>(wp, nwarps);
-}
-
 #define FIN_T 256
-// one CTA: fixed-order reduction of the warp partials (sum) and (value desc, index asc) selection
-__global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprWarpPartial *wp, int nwarps,
-                                                                   u64 n, PaprDevStats *out)
+// fixed-order reduction of the CTA partials (sum) and (value desc, index asc) selection; result in
+// thread 0 of the calling CTA
+__device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, PaprDevStats *out)
 {
     __shared__ double s_sum[FIN_T];
     __shared__ int s_val[PAPR_NTRACK][FIN_T];
@@ -317,7 +338,7 @@ __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprWa
     int val[PAPR_NTRACK];
     u64 idx[PAPR_NTRACK];
     for (int k = 0; k < PAPR_NTRACK; ++k) { val[k] = 0; idx[k] = 0; }
-    for (int i = t; i < nwarps; i += FIN_T) {
+    for (int i = t; i < nctas; i += FIN_T) {
         sum += wp[i].sum;
         for (int k = 0; k < PAPR_NTRACK; ++k)
             if (wp[i].val[k] > 0 && better(wp[i].val[k], wp[i].idx[k], val[k], idx[k])) {
@@ -347,19 +368,13 @@ __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprWa
     }
 }
 
-void papr_launch_stats_finalize(const PaprWarpPartial *wp, int nwarps, u64 n, PaprDevStats *out,
-                                cudaStream_t s)
-{
-    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nwarps, n, out);
-}
-
 // Merge the shards' pass-1 states in rank (= index) order and evaluate the reference's scalar
 // epilogue on the device:  avg = sum/offset (papr.c:131), ratio = peak/avg, L, and
 // level[j] = (float)(pow(10, x_j) * avg) (papr.c:139 / 170).  pow(10, x_j) and the least ratio for
 // which the reference's loops reach level j are tabulated once with the HOST libm, so only IEEE
 // double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
-__global__ void papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb, int graph,
-                                   PaprDevStats *merged, PaprDevLevels *lv)
+__device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
+                                 PaprDevStats *merged, PaprDevLevels *lv)
 {
     __shared__ int s_L;
     __shared__ double s_avg;
@@ -386,6 +401,7 @@ __global__ void papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTa
         lv->ratio = ratio;
         lv->L = lo;
         lv->graph = graph;
+        lv->status = 0;
         s_L = lo;
         s_avg = avg;
     }
@@ -394,10 +410,40 @@ __global__ void papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTa
         lv->level[j] = __double2float_rn(__dmul_rn(tb.pow10[j], s_avg));
 }
 
+// one CTA.  with_levels: single-shard analysis, the local state IS the merged state.
+__global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
+                                                                   PaprDevStats *out, bool with_levels,
+                                                                   PaprTables tb, int graph, PaprDevStats *merged,
+                                                                   PaprDevLevels *lv)
+{
+    reduce_partials(wp, nctas, n, out);
+    if (!with_levels) return;
+    __syncthreads(); // thread 0's global writes are read back by thread 0 only
+    merge_and_levels(out, 1, tb, graph, merged, lv);
+}
+
+void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, u64 n, PaprDevStats *out, cudaStream_t s)
+{
+    PaprTables none = {nullptr, nullptr, 0};
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, out, false, none, 0, nullptr, nullptr);
+}
+
+void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
+                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s)
+{
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, true, t, graph, merged, lv);
+}
+
+__global__ void __launch_bounds__(FIN_T) papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb,
+                                                           int graph, PaprDevStats *merged, PaprDevLevels *lv)
+{
+    merge_and_levels(parts, nparts, tb, graph, merged, lv);
+}
+
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
                         PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s)
 {
-    papr_levels_kernel<<<1, 256, 0, s>>>(parts, nparts, t, graph, merged, lv);
+    papr_levels_kernel<<<1, FIN_T, 0, s>>>(parts, nparts, t, graph, merged, lv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -410,10 +456,10 @@ __device__ __forceinline__ unsigned hash32(unsigned x)
 }
 
 // Every `stride`-th warp batch (at a hashed position inside its group, so a periodic capture cannot
-// alias with the stride).  Per warp: sum, sum of squares and count of the *batch* sums - batch means
+// alias with the stride).  Per CTA: sum, sum of squares and count of the *batch* sums - batch means
 // give an honest standard error even when neighbouring samples are correlated.
 __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_presample_kernel(const float *iq, u64 nsamples,
-                                                                         int stride, double *warp_pre)
+                                                                         int stride, double *cta_pre)
 {
     const int lane = threadIdx.x & 31;
     const unsigned gw = blockIdx.x * PAPR_WARPS + (threadIdx.x >> 5);
@@ -441,27 +487,33 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_presample_kernel(const f
         s2 += ls * ls;
         cnt += 1.0;
     }
-    if (lane == 0) {
-        warp_pre[3 * gw + 0] = s1;
-        warp_pre[3 * gw + 1] = s2;
-        warp_pre[3 * gw + 2] = cnt;
+    __shared__ double s_p[3][PAPR_WARPS];
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) { s_p[0][warp] = s1; s_p[1][warp] = s2; s_p[2][warp] = cnt; }
+    __syncthreads();
+    if (warp == 0) { // fixed-order fold of the warps -> one triple per CTA
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double x = warp_sum_fixed(lane < PAPR_WARPS ? s_p[k][lane] : 0.0);
+            if (lane == 0) cta_pre[3 * blockIdx.x + k] = x;
+        }
     }
 }
 
-void papr_launch_presample(const float *iq, u64 nsamples, int stride, int grid, double *warp_pre,
+void papr_launch_presample(const float *iq, u64 nsamples, int stride, int grid, double *cta_pre,
                            cudaStream_t s)
 {
-    papr_presample_kernel<<<grid, PAPR_THREADS, 0, s>>>(iq, nsamples, stride, warp_pre);
+    papr_presample_kernel<<<grid, PAPR_THREADS, 0, s>>>(iq, nsamples, stride, cta_pre);
 }
 
-__global__ void __launch_bounds__(1024) papr_presample_reduce_kernel(const double *warp_pre, int nwarps,
-                                                                     double *pre4)
+// fixed-order fold of the CTA triples; all threads of a 1024-thread CTA return {s1, s2, cnt}
+__device__ void reduce_pre(const double *cta_pre, int nctas, double out[3])
 {
     __shared__ double s[3][1024];
     const int t = threadIdx.x;
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int i = t; i < nwarps; i += 1024) {
-        a0 += warp_pre[3 * i]; a1 += warp_pre[3 * i + 1]; a2 += warp_pre[3 * i + 2];
+    for (int i = t; i < nctas; i += 1024) {
+        a0 += cta_pre[3 * i]; a1 += cta_pre[3 * i + 1]; a2 += cta_pre[3 * i + 2];
     }
     s[0][t] = a0; s[1][t] = a1; s[2][t] = a2;
     __syncthreads();
@@ -469,12 +521,20 @@ __global__ void __launch_bounds__(1024) papr_presample_reduce_kernel(const doubl
         if (t < o) { s[0][t] += s[0][t + o]; s[1][t] += s[1][t + o]; s[2][t] += s[2][t + o]; }
         __syncthreads();
     }
-    if (t == 0) { pre4[0] = s[0][0]; pre4[1] = s[1][0]; pre4[2] = s[2][0]; pre4[3] = 0.0; }
+    out[0] = s[0][0]; out[1] = s[1][0]; out[2] = s[2][0];
+    __syncthreads();
 }
 
-void papr_launch_presample_reduce(const double *warp_pre, int nwarps, double *pre4, cudaStream_t s)
+__global__ void __launch_bounds__(1024) papr_presample_reduce_kernel(const double *cta_pre, int nctas, double *pre4)
 {
-    papr_presample_reduce_kernel<<<1, 1024, 0, s>>>(warp_pre, nwarps, pre4);
+    double r[3];
+    reduce_pre(cta_pre, nctas, r);
+    if (threadIdx.x == 0) { pre4[0] = r[0]; pre4[1] = r[1]; pre4[2] = r[2]; pre4[3] = 0.0; }
+}
+
+void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s)
+{
+    papr_presample_reduce_kernel<<<1, 1024, 0, s>>>(cta_pre, nctas, pre4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,15 +552,27 @@ __device__ int assign_slots(const unsigned char *s_flag, int ncells, int sh, int
         int c = t * per + k;
         local += (c < ncells && s_flag[c]) ? 1 : 0;
     }
-    s_scan[t] = local;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan
-        int v = (t >= o) ? s_scan[t - o] : 0;
-        __syncthreads();
-        s_scan[t] += v;
-        __syncthreads();
+    // inclusive scan over the 1024 threads: shuffle scan inside each warp, then over the 32 warp totals
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, o);
+        if ((t & 31) >= o) incl += v;
     }
-    int ord = s_scan[t] - local;
+    if ((t & 31) == 31) s_scan[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+        int w = s_scan[t];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(FULL, w, o);
+            if (t >= o) w += v;
+        }
+        s_scan[32 + t] = w; // inclusive totals of warps 0..t
+    }
+    __syncthreads();
+    incl += (t >> 5) ? s_scan[32 + (t >> 5) - 1] : 0;
+    int ord = incl - local;
     for (int k = 0; k < per; ++k) {
         int c = t * per + k;
         unsigned fb = 0;
@@ -510,21 +582,28 @@ __device__ int assign_slots(const unsigned char *s_flag, int ncells, int sh, int
         }
         fine_base[c] = fb;
     }
-    int total = s_scan[1023];
+    int total = s_scan[63];
     __syncthreads();
     return total < max_slots ? total : max_slots;
 }
 
-// Fused mode.  pre4 = {sum, sum of squares, count} of batch sums (already reduced over ranks).
-__global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, PaprTables tb, float sigmas,
-                                                              int fine_slots, PaprPlan *plan,
-                                                              unsigned *fine_base)
+// Fused mode.  pre4 = {sum, sum of squares, count} of batch sums already reduced over ranks, or
+// (single shard) nctas > 0: fold this GPU's CTA triples here and skip the separate reduce launch.
+__global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, const double *cta_pre, int nctas,
+                                                              PaprTables tb, float sigmas, int fine_slots,
+                                                              PaprPlan *plan, unsigned *fine_base)
 {
     __shared__ unsigned char s_flag[PAPR_NCELLS_MAX];
     __shared__ int s_scan[1024];
     __shared__ int s_cov;
     const int t = threadIdx.x;
-    const double s1 = pre4[0], s2 = pre4[1], cnt = pre4[2];
+    double pre[3];
+    if (nctas > 0) {
+        reduce_pre(cta_pre, nctas, pre);
+    } else {
+        pre[0] = pre4[0]; pre[1] = pre4[1]; pre[2] = pre4[2];
+    }
+    const double s1 = pre[0], s2 = pre[1], cnt = pre[2];
     PaprPlan pl;
     pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
     pl.levels_covered = 0; pl.window = 0.f; pl.pad = 0; pl.avg_pred = 0.0;
@@ -573,11 +652,10 @@ __global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4
     }
 }
 
-void papr_launch_plan_pred(const double *pre4, PaprTables t, int graph, float sigmas, int fine_slots,
-                           PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
+void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas,
+                           int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
 {
-    (void)graph;
-    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, t, sigmas, fine_slots, plan, fine_base);
+    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, cta_pre, nctas, t, sigmas, fine_slots, plan, fine_base);
 }
 
 // Exact thresholds known (two-pass mode, or redo after a fused miss): ambiguous = the cells that hold
@@ -647,41 +725,11 @@ void papr_launch_zero_fine(const PaprPlan *plan, u64 *g_fine, int grid, cudaStre
 // ------------------------------------------------------------------------------------------------
 // resolve: cell histogram + fine table + exact thresholds -> level_count   (papr.c:147-151 restated)
 // ------------------------------------------------------------------------------------------------
-// g_hist[c] := number of samples in cells > c   (one CTA)
-__global__ void __launch_bounds__(1024) papr_suffix_kernel(const PaprPlan *plan, u64 *g_hist)
-{
-    __shared__ u64 s_scan[1024];
-    const PaprPlan pl = *plan;
-    if (!(pl.status & PLAN_HIST)) return;
-    const int t = threadIdx.x;
-    const int per = PAPR_NCELLS_MAX / 1024;
-    u64 v[PAPR_NCELLS_MAX / 1024];
-    u64 local = 0;
-    for (int k = 0; k < per; ++k) {
-        int c = t * per + k;
-        v[k] = c < pl.ncells ? g_hist[c] : 0;
-        local += v[k];
-    }
-    s_scan[t] = local;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) { // inclusive scan from the top: s_scan[t] = sum of threads >= t
-        u64 x = (t + o < 1024) ? s_scan[t + o] : 0;
-        __syncthreads();
-        s_scan[t] += x;
-        __syncthreads();
-    }
-    u64 above = s_scan[t] - local; // cells owned by higher threads
-    for (int k = per - 1; k >= 0; --k) {
-        int c = t * per + k;
-        if (c < pl.ncells) g_hist[c] = above;
-        above += v[k];
-    }
-}
-
-// one CTA per level (grid-stride): counts[j] = over + suffix[cell(T_j)] + sum of fine counters of the
-// values of that cell that are > T_j.  A threshold outside the planned cells / windows => RES_MISS.
+// one CTA per level (grid-stride): counts[j] = samples above the cell range + samples in the cells
+// above cell(T_j) + the fine counters of the values of that cell that are > T_j.  A threshold outside
+// the planned cells / windows => RES_MISS.
 __global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, const unsigned *fine_base,
-                                                         const PaprDevLevels *lv, const u64 *g_suffix,
+                                                         const PaprDevLevels *lv, const u64 *g_hist,
                                                          const u64 *g_fine, const u64 *g_over, u64 *counts,
                                                          int *status)
 {
@@ -702,22 +750,22 @@ __global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, c
         const u64 *f = g_fine + (fb - 1u);
         u64 acc = 0;
         for (unsigned k = (tb & fmask) + 1 + threadIdx.x; k <= fmask; k += 256) acc += f[k];
+        for (int c = d + 1 + threadIdx.x; c < pl.ncells; c += 256) acc += g_hist[c];
         s_red[threadIdx.x] = acc;
         __syncthreads();
         for (int o = 128; o > 0; o >>= 1) {
             if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
             __syncthreads();
         }
-        if (threadIdx.x == 0) counts[j] = s_red[0] + g_suffix[d] + *g_over;
+        if (threadIdx.x == 0) counts[j] = s_red[0] + *g_over;
         __syncthreads();
     }
 }
 
 void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
-                         u64 *g_hist, const u64 *g_fine, const u64 *g_over, u64 *counts, int *status,
+                         const u64 *g_hist, const u64 *g_fine, const u64 *g_over, u64 *counts, int *status,
                          int grid, cudaStream_t s)
 {
-    papr_suffix_kernel<<<1, 1024, 0, s>>>(plan, g_hist);
     papr_count_kernel<<<grid, 256, 0, s>>>(plan, fine_base, lv, g_hist, g_fine, g_over, counts, status);
 }
 

@@ -55,7 +55,7 @@ _lib = None
 # every symbol include/papr_b200.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", "papr_last_error",
                "papr_engine_stream", "papr_engine_set", "papr_main", "papr_analyze_host",
-               "papr_analyze_device", "papr_analyze_file", "papr_stats_device", "papr_stats_merge",
+               "papr_analyze_device", "papr_analyze_file", "papr_stats_device", "papr_stats_host", "papr_stats_merge",
                "papr_levels", "papr_ccdf_device", "papr_fused_presample", "papr_fused_scan",
                "papr_fused_counts", "papr_format", "papr_result_finish", "papr_siggen_device"]
 
@@ -84,6 +84,7 @@ def load_library(path: Optional[str] = None):
     lib.papr_analyze_device.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
     lib.papr_analyze_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(PaprResult)]
     lib.papr_stats_device.argtypes = [vp, vp, u64, u64, C.POINTER(PaprStats)]
+    lib.papr_stats_host.argtypes = [vp, vp, u64, u64, C.POINTER(PaprStats), C.POINTER(vp), C.POINTER(u64)]
     lib.papr_stats_merge.argtypes = [C.POINTER(PaprStats), C.POINTER(PaprStats)]
     lib.papr_stats_merge.restype = None
     lib.papr_levels.argtypes = [C.POINTER(PaprStats), i32, C.POINTER(C.c_double), C.POINTER(C.c_float),
@@ -226,6 +227,13 @@ class Engine:
                     "papr_stats_device")
         return st
 
+    def stats_shard_host(self, image, nbytes: int, first_index: int = 0):
+        """-> (stats, device address of the now-resident shard, samples)"""
+        st, dp, ns = PaprStats(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.papr_stats_host(self.h, _ptr(image), nbytes, first_index, C.byref(st), C.byref(dp),
+                                             C.byref(ns)), "papr_stats_host")
+        return st, dp.value or 0, ns.value
+
     def ccdf_shard(self, d_iq, nsamples: int, level: Sequence[float]):
         L = len(level)
         lv = (C.c_float * max(L, 1))(*level)
@@ -260,7 +268,7 @@ class Engine:
 
 # ---- byte-range sharding over ranks (one process per GPU, torch.distributed) -----------------------
 def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, mode: int = MODE_TWO_PASS,
-                    group=None) -> PaprResult:
+                    group=None, host_image=None) -> PaprResult:
     """Each rank holds samples [first_index, first_index+nsamples) of one capture; ranks are in index
     order.  Two tiny exchanges, no data-path collective: all-gather of the pass-1 states (merged in
     rank order on every rank, so first occurrences and the level table are identical everywhere) and
@@ -298,7 +306,10 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
         v = t.tolist()
         return v[:-1], v[-1]
 
-    if mode == MODE_FUSED:
+    if host_image is not None:  # shard in (pinned) host memory: H2D + pass 1 overlapped, then resident
+        mode = MODE_TWO_PASS
+        local, d_iq, nsamples = engine.stats_shard_host(host_image, nsamples * 8, first_index)
+    elif mode == MODE_FUSED:
         pre = allreduce_f64(engine.fused_presample(d_iq, nsamples, graph))
         local = engine.fused_scan(d_iq, nsamples, first_index, pre, graph)
     else:

