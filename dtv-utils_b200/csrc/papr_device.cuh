@@ -68,12 +68,12 @@ struct PaprDevLevels {
     double ratio;       // (double)peak / avg
     int L;
     int graph;
-    int status;         // RES_* bits set by the resolve kernel; cleared whenever the levels are (re)written
-    int pad;
+    int pad[2];
     float level[PAPR_MAX_LEVELS];
 };
 
-// status word written by the resolve kernel
+// status word written by the resolve kernel; it lives right after the level counts
+// (counts[PAPR_MAX_LEVELS]) so that one all-reduce(sum) carries both across ranks
 enum { RES_MISS = 1 };
 
 struct PaprScanArgs {
@@ -99,9 +99,10 @@ void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cu
 void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprDevStats *out,
                                 cudaStream_t s);
 void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
-                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s);
+                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
+                                 unsigned long long *status_word, cudaStream_t s);
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
-                        PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s);
+                        PaprDevStats *merged, PaprDevLevels *lv, unsigned long long *status_word, cudaStream_t s);
 void papr_launch_presample(const float *iq, unsigned long long nsamples, int stride, int grid,
                            double *cta_pre /* [grid*3] */, cudaStream_t s);
 void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s);
@@ -113,7 +114,7 @@ void papr_launch_zero_fine(const PaprPlan *plan, unsigned long long *g_fine, int
 void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
                          const unsigned long long *g_hist,
                          const unsigned long long *g_fine, const unsigned long long *g_over,
-                         unsigned long long *counts, int *status, int grid, cudaStream_t s);
+                         unsigned long long *counts, unsigned long long *status_word, int grid, cudaStream_t s);
 void papr_launch_bsearch(const float *iq, unsigned long long nsamples, const PaprPlan *plan,
                          const PaprDevLevels *lv, unsigned long long *bhist, int grid, cudaStream_t s);
 void papr_launch_bsearch_counts(const PaprPlan *plan, const PaprDevLevels *lv,

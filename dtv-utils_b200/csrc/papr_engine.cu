@@ -53,7 +53,7 @@ struct DevOut {
     PaprDevStats local;   // this shard
     PaprDevStats merged;  // all shards (single-shard analysis: == local)
     PaprPlan plan;
-    u64 counts[PAPR_MAX_LEVELS + 1];
+    u64 counts[PAPR_MAX_LEVELS + 1]; // [PAPR_MAX_LEVELS] = status word (RES_* bits, summed over ranks)
     PaprDevLevels lv;
 };
 
@@ -162,6 +162,7 @@ struct papr_engine {
     int scan_pairs = 0;
     unsigned launches = 0;
     u64 h2d = 0, d2h = 0;
+    int shard_mode = PAPR_MODE_TWO_PASS; // of the stream-ordered shard stages in flight
 
     PaprTables tables(int graph) const
     {
@@ -336,7 +337,7 @@ static int enqueue_scan(papr_engine *e, bool stats, bool hist, const float *d_iq
 static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph)
 {
     papr_launch_finalize_levels(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                &e->d_out->lv, e->stream);
+                                &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
@@ -345,7 +346,7 @@ static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph)
 static int enqueue_resolve(papr_engine *e)
 {
     papr_launch_resolve(&e->d_out->plan, e->d_fine_base, &e->d_out->lv, e->d_work->hist, e->d_fine, &e->d_work->over,
-                        e->d_out->counts, &e->d_out->lv.status, e->num_sms * 2, e->stream);
+                        e->d_out->counts, &e->d_out->counts[PAPR_MAX_LEVELS], e->num_sms * 2, e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
@@ -468,7 +469,7 @@ static int collect(papr_engine *e, int graph, papr_result *out, bool counts_vali
     if (out->nlevels > 0) {
         bool same = h->lv.L == out->nlevels &&
                     memcmp(h->lv.level, out->level, sizeof(float) * (size_t)out->nlevels) == 0;
-        if (!same || !counts_valid || (h->lv.status & RES_MISS)) redo = 1;
+        if (!same || !counts_valid || (h->counts[PAPR_MAX_LEVELS] != 0)) redo = 1;
         if (!redo)
             for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)h->counts[j];
     }
@@ -481,12 +482,13 @@ static int upload_levels(papr_engine *e, const float *level, int L, float peak)
     static thread_local PaprDevStats ms;
     memset(&ms, 0, sizeof(ms));
     memcpy(&ms.val[TR_PEAK], &peak, 4);
-    lv.avg = 0; lv.ratio = 0; lv.L = L; lv.graph = 0; lv.status = 0; lv.pad = 0;
+    lv.avg = 0; lv.ratio = 0; lv.L = L; lv.graph = 0; lv.pad[0] = lv.pad[1] = 0;
     memcpy(lv.level, level, sizeof(float) * (size_t)L);
     // pageable -> the runtime stages these synchronously, so the thread_local sources may be reused
     CU(cudaMemcpyAsync(&e->d_out->lv, &lv, offsetof(PaprDevLevels, level) + sizeof(float) * (size_t)L,
                        cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(&e->d_out->merged, &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemsetAsync(&e->d_out->counts[PAPR_MAX_LEVELS], 0, sizeof(u64), e->stream));
     e->h2d += sizeof(float) * (size_t)L + sizeof(ms);
     return PAPR_OK;
 }
@@ -503,7 +505,7 @@ static int run_exact_ccdf(papr_engine *e, const float *d_iq, u64 n, const float 
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaStreamSynchronize(e->stream));
     const DevOut *h = &e->h_out->o;
-    if (h->lv.status & RES_MISS) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+    if (h->counts[PAPR_MAX_LEVELS] != 0) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
     for (int j = 0; j < L; ++j) {
         if (accumulate) level_count[j] += (int64_t)h->counts[j];
         else level_count[j] = (int64_t)h->counts[j];
@@ -652,7 +654,8 @@ extern "C" int papr_fused_counts(papr_engine *e, const papr_stats *merged, int g
     PaprDevStats ms;
     stats_to_device(*merged, &ms);
     CU(cudaMemcpyAsync(&e->d_out->local, &ms, sizeof(ms), cudaMemcpyHostToDevice, e->stream));
-    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv, e->stream);
+    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
+                       &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
     e->launches += 1;
     int rc;
     if ((rc = enqueue_resolve(e))) return rc;
@@ -662,6 +665,95 @@ extern "C" int papr_fused_counts(papr_engine *e, const papr_stats *merged, int g
     if (collect(e, graph, &r, true)) return 1; // miss: caller runs papr_ccdf_device on every shard
     for (int j = 0; j < r.nlevels; ++j) level_count[j] += r.level_count[j];
     return PAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream-ordered shard stages (no host synchronisation until papr_shard_finish): the caller enqueues
+// its collectives (NCCL) on papr_engine_stream() between them, directly on the engine's buffers.
+// ------------------------------------------------------------------------------------------------
+extern "C" int papr_engine_device_buffer(papr_engine *e, int which, void **ptr, uint64_t *bytes)
+{
+    if (!e || !ptr || !bytes) return PAPR_ERR_ARG;
+    switch (which) {
+    case PAPR_BUF_PRESAMPLE: *ptr = e->d_pre4; *bytes = 4 * sizeof(double); break;
+    case PAPR_BUF_LOCAL_STATS: *ptr = &e->d_out->local; *bytes = sizeof(PaprDevStats); break;
+    case PAPR_BUF_COUNTS: *ptr = e->d_out->counts; *bytes = sizeof(u64) * (PAPR_MAX_LEVELS + 1); break;
+    default: return fail(e, PAPR_ERR_ARG, "unknown buffer id");
+    }
+    return PAPR_OK;
+}
+
+extern "C" int papr_shard_presample_async(papr_engine *e, const float *d_iq, uint64_t n, int graph)
+{
+    if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
+    begin_analysis(e);
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
+                          presample_stride_for(e, n, graph ? 1 : 0), e->grid, e->d_pre_cta, e->stream);
+    papr_launch_presample_reduce(e->d_pre_cta, e->grid, e->d_pre4, e->stream);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+extern "C" int papr_shard_scan_async(papr_engine *e, const float *d_iq, uint64_t n, uint64_t first, int graph, int fused)
+{
+    if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    graph = graph ? 1 : 0;
+    int rc;
+    e->shard_mode = fused ? PAPR_MODE_FUSED : PAPR_MODE_TWO_PASS;
+    if (!fused) {
+        begin_analysis(e);
+        CU(cudaEventRecord(e->ev_begin, e->stream));
+    }
+    if ((rc = enqueue_reset(e))) return rc;
+    if (fused) {
+        papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas,
+                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
+        papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
+        e->launches += 2;
+    }
+    if ((rc = enqueue_scan(e, true, fused != 0, d_iq, n, first, true))) return rc;
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
+    e->launches += 1;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+extern "C" int papr_shard_counts_async(papr_engine *e, const void *d_all_stats, int nparts, int graph, int fused,
+                                       const float *d_iq, uint64_t n)
+{
+    if (!e || !d_all_stats || nparts < 1) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    int rc;
+    papr_launch_levels((const PaprDevStats *)d_all_stats, nparts, e->tables(graph), graph, &e->d_out->merged,
+                       &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
+    e->launches += 1;
+    if (fused) {
+        if ((rc = enqueue_resolve(e))) return rc;
+    } else {
+        CU(cudaMemsetAsync(e->d_work, 0, offsetof(DevWork, wp), e->stream)); // histogram scratch only
+        if ((rc = enqueue_hist_exact(e, d_iq, n, true))) return rc;
+    }
+    return PAPR_OK;
+}
+
+extern "C" int papr_shard_finish(papr_engine *e, int graph, papr_result *out)
+{
+    if (!e || !out) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    int rc;
+    memset(out, 0, offsetof(papr_result, level));
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->o.merged, &out->stats);
+    int redo = collect(e, graph, out, true);
+    finish_timing(e, out);
+    out->mode_used = e->shard_mode;
+    out->fused_miss = redo;
+    return redo; // 1: run papr_shard_counts_async(..., fused = 0, ...) on every rank, reduce, finish again
 }
 
 extern "C" int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first, uint64_t n, uint64_t seed)

@@ -374,7 +374,7 @@ __device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, Papr
 // which the reference's loops reach level j are tabulated once with the HOST libm, so only IEEE
 // double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
 __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
-                                 PaprDevStats *merged, PaprDevLevels *lv)
+                                 PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word)
 {
     __shared__ int s_L;
     __shared__ double s_avg;
@@ -401,7 +401,7 @@ __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const Pa
         lv->ratio = ratio;
         lv->L = lo;
         lv->graph = graph;
-        lv->status = 0;
+        *status_word = 0; // RES_* bits of the resolve that follows
         s_L = lo;
         s_avg = avg;
     }
@@ -414,36 +414,38 @@ __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const Pa
 __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
                                                                    PaprDevStats *out, bool with_levels,
                                                                    PaprTables tb, int graph, PaprDevStats *merged,
-                                                                   PaprDevLevels *lv)
+                                                                   PaprDevLevels *lv, u64 *status_word)
 {
     reduce_partials(wp, nctas, n, out);
     if (!with_levels) return;
     __syncthreads(); // thread 0's global writes are read back by thread 0 only
-    merge_and_levels(out, 1, tb, graph, merged, lv);
+    merge_and_levels(out, 1, tb, graph, merged, lv, status_word);
 }
 
 void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, u64 n, PaprDevStats *out, cudaStream_t s)
 {
     PaprTables none = {nullptr, nullptr, 0};
-    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, out, false, none, 0, nullptr, nullptr);
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, out, false, none, 0, nullptr, nullptr, nullptr);
 }
 
 void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
-                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s)
+                                 PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
+                                 u64 *status_word, cudaStream_t s)
 {
-    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, true, t, graph, merged, lv);
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, true, t, graph, merged, lv, status_word);
 }
 
 __global__ void __launch_bounds__(FIN_T) papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb,
-                                                           int graph, PaprDevStats *merged, PaprDevLevels *lv)
+                                                           int graph, PaprDevStats *merged, PaprDevLevels *lv,
+                                                           u64 *status_word)
 {
-    merge_and_levels(parts, nparts, tb, graph, merged, lv);
+    merge_and_levels(parts, nparts, tb, graph, merged, lv, status_word);
 }
 
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
-                        PaprDevStats *merged, PaprDevLevels *lv, cudaStream_t s)
+                        PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word, cudaStream_t s)
 {
-    papr_levels_kernel<<<1, FIN_T, 0, s>>>(parts, nparts, t, graph, merged, lv);
+    papr_levels_kernel<<<1, FIN_T, 0, s>>>(parts, nparts, t, graph, merged, lv, status_word);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -731,7 +733,7 @@ void papr_launch_zero_fine(const PaprPlan *plan, u64 *g_fine, int grid, cudaStre
 __global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, const unsigned *fine_base,
                                                          const PaprDevLevels *lv, const u64 *g_hist,
                                                          const u64 *g_fine, const u64 *g_over, u64 *counts,
-                                                         int *status)
+                                                         u64 *status_word)
 {
     __shared__ u64 s_red[256];
     const PaprPlan pl = *plan;
@@ -743,7 +745,7 @@ __global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, c
         bool in = (pl.status & PLAN_HIST) && (unsigned)d < (unsigned)pl.ncells;
         unsigned fb = in ? fine_base[d] : 0;
         if (!fb) {
-            if (threadIdx.x == 0) { atomicOr(status, RES_MISS); counts[j] = 0; }
+            if (threadIdx.x == 0) { atomicOr(status_word, (u64)RES_MISS); counts[j] = 0; }
             continue;
         }
         const unsigned fmask = (1u << pl.sh) - 1u;
@@ -763,10 +765,10 @@ __global__ void __launch_bounds__(256) papr_count_kernel(const PaprPlan *plan, c
 }
 
 void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const PaprDevLevels *lv,
-                         const u64 *g_hist, const u64 *g_fine, const u64 *g_over, u64 *counts, int *status,
+                         const u64 *g_hist, const u64 *g_fine, const u64 *g_over, u64 *counts, u64 *status_word,
                          int grid, cudaStream_t s)
 {
-    papr_count_kernel<<<grid, 256, 0, s>>>(plan, fine_base, lv, g_hist, g_fine, g_over, counts, status);
+    papr_count_kernel<<<grid, 256, 0, s>>>(plan, fine_base, lv, g_hist, g_fine, g_over, counts, status_word);
 }
 
 // ------------------------------------------------------------------------------------------------

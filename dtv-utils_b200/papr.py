@@ -57,7 +57,10 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_engine_stream", "papr_engine_set", "papr_main", "papr_analyze_host",
                "papr_analyze_device", "papr_analyze_file", "papr_stats_device", "papr_stats_host", "papr_stats_merge",
                "papr_levels", "papr_ccdf_device", "papr_fused_presample", "papr_fused_scan",
-               "papr_fused_counts", "papr_format", "papr_result_finish", "papr_siggen_device"]
+               "papr_fused_counts", "papr_format", "papr_result_finish", "papr_siggen_device",
+               "papr_engine_device_buffer", "papr_shard_presample_async", "papr_shard_scan_async",
+               "papr_shard_counts_async", "papr_shard_finish"]
+BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
 def load_library(path: Optional[str] = None):
@@ -97,6 +100,11 @@ def load_library(path: Optional[str] = None):
     lib.papr_format.restype = C.c_long
     lib.papr_result_finish.argtypes = [C.POINTER(PaprResult), i32]
     lib.papr_siggen_device.argtypes = [vp, vp, u64, u64, u64]
+    lib.papr_engine_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    lib.papr_shard_presample_async.argtypes = [vp, vp, u64, i32]
+    lib.papr_shard_scan_async.argtypes = [vp, vp, u64, u64, i32, i32]
+    lib.papr_shard_counts_async.argtypes = [vp, vp, i32, i32, i32, vp, u64]
+    lib.papr_shard_finish.argtypes = [vp, i32, C.POINTER(PaprResult)]
     if path is None:
         _lib = lib
     return lib
@@ -261,6 +269,40 @@ class Engine:
                          "papr_fused_counts")
         return rc == 1, cnt
 
+    # stream-ordered stages (see include/papr_b200.h) ---------------------------------------------------
+    def device_buffer(self, which: int, dtype):
+        """torch tensor aliasing one of the engine's exchange buffers (zero copy)."""
+        import torch
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.papr_engine_device_buffer(self.h, which, C.byref(ptr), C.byref(nbytes)),
+                    "papr_engine_device_buffer")
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        typestr = {torch.float64: "<f8", torch.int64: "<i8", torch.uint8: "|u1"}[dtype]
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (nbytes.value // itemsize,), "typestr": typestr,
+                                        "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Alias(), device="cuda")
+
+    def shard_presample_async(self, d_iq, nsamples: int, graph: bool):
+        self._check(self.lib.papr_shard_presample_async(self.h, _ptr(d_iq), nsamples, int(bool(graph))),
+                    "papr_shard_presample_async")
+
+    def shard_scan_async(self, d_iq, nsamples: int, first_index: int, graph: bool, fused: bool):
+        self._check(self.lib.papr_shard_scan_async(self.h, _ptr(d_iq), nsamples, first_index, int(bool(graph)),
+                                                   int(bool(fused))), "papr_shard_scan_async")
+
+    def shard_counts_async(self, d_all_stats, nparts: int, graph: bool, fused: bool, d_iq, nsamples: int):
+        self._check(self.lib.papr_shard_counts_async(self.h, _ptr(d_all_stats), nparts, int(bool(graph)),
+                                                     int(bool(fused)), _ptr(d_iq), nsamples),
+                    "papr_shard_counts_async")
+
+    def shard_finish(self, graph: bool):
+        """-> (miss, result of the whole capture)"""
+        res = PaprResult()
+        rc = self._check(self.lib.papr_shard_finish(self.h, int(bool(graph)), C.byref(res)), "papr_shard_finish")
+        return rc == 1, res
+
     def siggen(self, d_out, first_index: int, nsamples: int, seed: int):
         self._check(self.lib.papr_siggen_device(self.h, _ptr(d_out), first_index, nsamples, seed),
                     "papr_siggen_device")
@@ -279,6 +321,8 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     backend = dist.get_backend(group) if dist.is_initialized() else "none"
+    if backend == "nccl" and isinstance(engine, Engine) and host_image is None:
+        return _analyze_sharded_stream_ordered(engine, d_iq, nsamples, first_index, bool(graph), mode, group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     graph = bool(graph)
 
@@ -326,6 +370,42 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
         if miss:  # two-pass mode, or some rank's thresholds fell outside its predicted windows
             counts, _ = allreduce_counts(engine.ccdf_shard(d_iq, nsamples, lv))
     return result_from_parts(merged, graph, counts)
+
+
+def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group):
+    """NCCL path: kernels and the three tiny collectives are enqueued back to back on the engine's
+    stream, operating in place on the engine's device buffers; one host synchronisation at the end."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    fused = mode != MODE_TWO_PASS
+    st = getattr(engine, "_xchg", None)
+    if st is None:
+        st = engine._xchg = {
+            "stream": torch.cuda.ExternalStream(engine.stream),
+            "pre": engine.device_buffer(BUF_PRESAMPLE, torch.float64),
+            "local": engine.device_buffer(BUF_LOCAL_STATS, torch.uint8),
+            "counts": engine.device_buffer(BUF_COUNTS, torch.int64),
+        }
+        st["all"] = torch.empty(world * st["local"].numel(), dtype=torch.uint8, device="cuda")
+    with torch.cuda.stream(st["stream"]):
+        if fused:
+            engine.shard_presample_async(d_iq, nsamples, graph)
+            dist.all_reduce(st["pre"], group=group)
+        engine.shard_scan_async(d_iq, nsamples, first_index, graph, fused)
+        dist.all_gather_into_tensor(st["all"], st["local"], group=group)
+        engine.shard_counts_async(st["all"], world, graph, fused, d_iq, nsamples)
+        dist.all_reduce(st["counts"], group=group)
+        miss, res = engine.shard_finish(graph)
+        if miss:  # some rank's thresholds fell outside its predicted windows: exact pass everywhere
+            engine.shard_counts_async(st["all"], world, graph, False, d_iq, nsamples)
+            dist.all_reduce(st["counts"], group=group)
+            miss2, res = engine.shard_finish(graph)
+            if miss2:
+                raise PaprError("exact CCDF pass reported a miss")
+            res.fused_miss = 1
+    return res
 
 
 # ---- the process boundary --------------------------------------------------------------------------

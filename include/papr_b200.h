@@ -139,6 +139,23 @@ int papr_fused_scan(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64
                     const double pre[4], int graph, papr_stats *out);
 int papr_fused_counts(papr_engine *e, const papr_stats *merged, int graph, int64_t *level_count);
 
+/* Stream-ordered variants of the shard stages: nothing synchronises with the host until
+ * papr_shard_finish, so a caller (one process per GPU) interleaves its collectives on
+ * papr_engine_stream() directly on the engine's device buffers:
+ *     presample_async -> all-reduce(sum) of PAPR_BUF_PRESAMPLE (4 doubles)          [fused only]
+ *     scan_async      -> all-gather of PAPR_BUF_LOCAL_STATS (opaque, device format) into d_all_stats
+ *     counts_async    -> all-reduce(sum) of PAPR_BUF_COUNTS (PAPR_MAX_LEVELS+1 u64: counts + miss word)
+ *     finish          -> result of the WHOLE capture; returns 1 if any rank missed (then call
+ *                        counts_async with fused = 0, reduce and finish again). */
+enum { PAPR_BUF_PRESAMPLE = 0, PAPR_BUF_LOCAL_STATS = 1, PAPR_BUF_COUNTS = 2 };
+int papr_engine_device_buffer(papr_engine *e, int which, void **ptr, uint64_t *bytes);
+int papr_shard_presample_async(papr_engine *e, const float *d_iq, uint64_t nsamples, int graph);
+int papr_shard_scan_async(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index, int graph,
+                          int fused);
+int papr_shard_counts_async(papr_engine *e, const void *d_all_stats, int nparts, int graph, int fused,
+                            const float *d_iq, uint64_t nsamples);
+int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
+
 /* papr.c:132-135,154-161 / 186-190: the exact stdout text.  Returns its length, or <0. */
 long papr_format(const papr_result *r, char *out, size_t cap);
 /* Fill avg/papr/levels of `r` from r->stats (papr_levels) — for callers that merged shards. */
