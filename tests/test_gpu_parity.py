@@ -209,3 +209,37 @@ def test_full_size_properties(built, eng, torch_cuda, log2n):
     # Appendix-A known answer on the first 2^20 samples of the same stream (seed 1)
     head = eng.analyze_device(d, 1 << 20, False)
     assert built.format_result(head) == _gold("appA_1M", False)
+
+
+# ---- BASELINE configs[1] at full size against the REAL reference binary ------------------------------
+def test_config1_4gib_cli_vs_reference_binary(built, eng, torch_cuda, tmp_path_factory):
+    """`papr` on a 4 GiB synthetic capture (2^29 samples, seed 1): stdout of the drop-in CLI must be
+    identical to stdout of the unmodified reference binary (oracle/_ref/papr, ~20 s of CPU)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "papr")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/papr not present")
+    import shutil
+    if shutil.disk_usage("/dev/shm").free < (5 << 30):
+        pytest.skip("not enough tmpfs for a 4 GiB capture")
+    n = 1 << 29
+    path = "/dev/shm/papr_b200_test_4gib_%d.cfile" % os.getpid()
+    try:
+        d = torch_cuda.empty(2 * n, dtype=torch_cuda.float32, device="cuda:0")
+        eng.siggen(d, 0, n, 1)
+        with open(path, "wb") as f:
+            step = 1 << 26
+            for k in range(0, 2 * n, step):
+                f.write(d[k:k + step].cpu().numpy().tobytes())
+        want = subprocess.run([ref, path], capture_output=True).stdout
+        got = subprocess.run([built.cli_path(), path], capture_output=True)
+        assert got.returncode == 0 and got.stdout == want
+        for mode in (1, 2):  # and the device-resident paths, both schedules
+            eng.set("mode", mode)
+            assert built.format_result(eng.analyze_device(d, n, False)) == want
+        eng.set("mode", 0)
+        if os.environ.get("PAPR_B200_TEST_GRAPH_4GIB"):  # ~2 min of CPU for the reference
+            want_g = subprocess.run([ref, "-g", path], capture_output=True).stdout
+            assert subprocess.run([built.cli_path(), "-g", path], capture_output=True).stdout == want_g
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
