@@ -27,6 +27,9 @@
 #define PAPR_SH_MIN 12                         // finest cell: 2^12 float32 values (2048 cells / octave)
 #define PAPR_SH_MAX 23
 #define PAPR_NTRACK 5                          // peak power, +I, -I, +Q, -Q
+#define PAPR_SEQ_TILE 32768                    // samples per tile of the exact sequential-sum emulation
+#define PAPR_SEQ_ZERO 30000                    // tile code: all samples zero (identity)
+#define PAPR_SEQ_DIRTY 30001                   // tile code: may cross a power of two -> replayed on the host
 
 // order of the five extreme trackers everywhere on the device
 enum { TR_PEAK = 0, TR_RE_POS = 1, TR_RE_NEG = 2, TR_IM_POS = 3, TR_IM_NEG = 4 };
@@ -124,5 +127,9 @@ void papr_launch_siggen(float *iq, unsigned long long first, unsigned long long 
                         unsigned long long seed, int grid, cudaStream_t s);
 void papr_launch_find_nan(const float *iq, unsigned long long nsamples, unsigned long long first_index,
                           unsigned long long *out_idx, int grid, cudaStream_t s);
+void papr_launch_tilesum(const float *iq, unsigned long long nsamples, double *tile_sum, int grid, cudaStream_t s);
+void papr_launch_seqsum(const float *iq, unsigned long long nsamples, const short *tile_code,
+                        void *tile_run /* {u64 d0, d1}[ntiles] */, int grid, cudaStream_t s);
+int papr_seqsum_configure(void);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

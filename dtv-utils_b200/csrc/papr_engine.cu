@@ -139,6 +139,14 @@ struct papr_engine {
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
+    int exact_sum = -1;       // -1: on for the file/host path, off for device-resident; 0 off; 1 on
+    // exact sequential-sum scratch (grown on demand)
+    u64 seq_tiles = 0;
+    double *d_tile_sum = nullptr, *h_tile_sum = nullptr;
+    short *d_tile_code = nullptr, *h_tile_code = nullptr;
+    u64 *d_tile_run = nullptr, *h_tile_run = nullptr;
+    float *h_tile_data = nullptr;
+    unsigned seq_dirty = 0;
     // device work buffers
     int grid = 0;
     DevWork *d_work = nullptr;
@@ -213,7 +221,8 @@ static int engine_init(papr_engine *e, int device)
     e->num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    if (papr_scan_configure() != 0) return fail(e, PAPR_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed");
+    if (papr_scan_configure() != 0 || papr_seqsum_configure() != 0)
+        return fail(e, PAPR_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed");
     e->grid = e->num_sms * e->grid_per_sm;
     if (e->grid > kMaxGrid) return fail(e, PAPR_ERR_CUDA, "more SMs than this build supports");
     CU(cudaMalloc(&e->d_work, sizeof(DevWork)));
@@ -261,7 +270,11 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     delete e->pool;
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_work); cudaFree(e->d_out); cudaFree(e->d_nan_idx); cudaFree(e->d_fine_base); cudaFree(e->d_fine);
-    cudaFree(e->d_pre_cta);
+    cudaFree(e->d_pre_cta); cudaFree(e->d_tile_sum); cudaFree(e->d_tile_code); cudaFree(e->d_tile_run);
+    if (e->h_tile_sum) cudaFreeHost(e->h_tile_sum);
+    if (e->h_tile_code) cudaFreeHost(e->h_tile_code);
+    if (e->h_tile_run) cudaFreeHost(e->h_tile_run);
+    if (e->h_tile_data) cudaFreeHost(e->h_tile_data);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
     if (e->h_out) cudaFreeHost(e->h_out);
     for (auto &p : e->h_stage) if (p) cudaFreeHost(p);
@@ -285,6 +298,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(size_t)((PAPR_BATCH_SAMPLES * 8) - 1));
     else if (n == "staging_threads") { e->staging_threads = std::max(0, (int)v); delete e->pool; e->pool = nullptr; }
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
+    else if (n == "exact_sum") e->exact_sum = (int)v;
     else if (n == "fine_bytes_log2") e->fine_bytes_log2 = std::min(26, std::max(4, (int)v)); // <= the allocation
     else if (n == "grid_per_sm") return fail(e, PAPR_ERR_ARG, "grid_per_sm is fixed at engine creation");
     else return fail(e, PAPR_ERR_ARG, "unknown tunable: " + n);
@@ -526,6 +540,121 @@ static void finish_timing(papr_engine *e, papr_result *out)
 }
 
 // ------------------------------------------------------------------------------------------------
+// exact sequential sum (papr.c:104): see papr_seqsum_kernel.  Returns 1 if not applicable (NaN/Inf).
+// ------------------------------------------------------------------------------------------------
+static int ensure_seq_buffers(papr_engine *e, u64 ntiles)
+{
+    if (ntiles <= e->seq_tiles) return PAPR_OK;
+    cudaFree(e->d_tile_sum); cudaFree(e->d_tile_code); cudaFree(e->d_tile_run);
+    if (e->h_tile_sum) cudaFreeHost(e->h_tile_sum);
+    if (e->h_tile_code) cudaFreeHost(e->h_tile_code);
+    if (e->h_tile_run) cudaFreeHost(e->h_tile_run);
+    e->seq_tiles = 0;
+    u64 cap = std::max<u64>(ntiles, 4096);
+    CU(cudaMalloc(&e->d_tile_sum, cap * sizeof(double)));
+    CU(cudaMalloc(&e->d_tile_code, cap * sizeof(short)));
+    CU(cudaMalloc(&e->d_tile_run, cap * 2 * sizeof(u64)));
+    CU(cudaHostAlloc(&e->h_tile_sum, cap * sizeof(double), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&e->h_tile_code, cap * sizeof(short), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&e->h_tile_run, cap * 2 * sizeof(u64), cudaHostAllocDefault));
+    if (!e->h_tile_data) CU(cudaHostAlloc(&e->h_tile_data, (size_t)PAPR_SEQ_TILE * 8, cudaHostAllocDefault));
+    e->seq_tiles = cap;
+    return PAPR_OK;
+}
+
+static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double *sum_out)
+{
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    if (ntiles == 0) { *sum_out = 0.0; return PAPR_OK; }
+    int rc;
+    if ((rc = ensure_seq_buffers(e, ntiles))) return rc;
+    // 1. tile sums -> which binade each tile's running sum lives in
+    papr_launch_tilesum(d_iq, n, e->d_tile_sum, e->num_sms * 2, e->stream);
+    CU(cudaMemcpyAsync(e->h_tile_sum, e->d_tile_sum, ntiles * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    double pre = 0.0;
+    for (u64 t = 0; t < ntiles; ++t) {
+        const double ts = e->h_tile_sum[t];
+        if (!std::isfinite(ts)) return 1; // the reference's sum is NaN/Inf as well: nothing to emulate
+        short code = PAPR_SEQ_DIRTY;
+        if (ts == 0.0) {
+            code = PAPR_SEQ_ZERO;
+        } else {
+            const double lo = pre * (1.0 - 1e-9), hi = (pre + ts) * (1.0 + 1e-9);
+            if (lo > 0.0) {
+                const int k = std::ilogb(lo);
+                if (hi < std::ldexp(1.0, k + 1)) code = (short)k;
+            }
+        }
+        e->h_tile_code[t] = code;
+        pre += ts;
+    }
+    // 2. (D0, D1) of every clean tile
+    CU(cudaMemcpyAsync(e->d_tile_code, e->h_tile_code, ntiles * sizeof(short), cudaMemcpyHostToDevice, e->stream));
+    papr_launch_seqsum(d_iq, n, e->d_tile_code, e->d_tile_run, e->num_sms, e->stream);
+    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->launches += 2;
+    e->d2h += ntiles * 24;
+    e->h2d += ntiles * 2;
+    // 3. chain the tiles in file order; anything not provably inside its binade is replayed literally
+    double s = 0.0;
+    e->seq_dirty = 0;
+    for (u64 t = 0; t < ntiles; ++t) {
+        const short code = e->h_tile_code[t];
+        if (code == PAPR_SEQ_ZERO) continue;
+        if (code != PAPR_SEQ_DIRTY) {
+            const int k = code;
+            if (s >= std::ldexp(1.0, k) && s < std::ldexp(1.0, k + 1)) {
+                const u64 m = (u64)std::ldexp(s, 52 - k); // exact: s is a multiple of 2^(k-52)
+                const u64 m2 = m + ((m & 1) ? e->h_tile_run[2 * t + 1] : e->h_tile_run[2 * t]);
+                if (m2 < (1ull << 53)) {
+                    s = std::ldexp((double)m2, k - 52);
+                    continue;
+                }
+            }
+        }
+        const u64 first = t * PAPR_SEQ_TILE, cnt = std::min<u64>(PAPR_SEQ_TILE, n - first);
+        CU(cudaMemcpyAsync(e->h_tile_data, d_iq + 2 * first, cnt * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        s = papr_host_seq_add(s, e->h_tile_data, cnt);
+        e->seq_dirty++;
+        e->d2h += cnt * 8;
+    }
+    *sum_out = s;
+    return PAPR_OK;
+}
+
+// replace the tree sum of the local (== whole capture) state by the exact sequential one
+static int apply_exact_sum(papr_engine *e, const float *d_iq, u64 n)
+{
+    double s = 0.0;
+    int rc = exact_sequential_sum(e, d_iq, n, &s);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+        e->h_out->pre4[0] = s;
+        CU(cudaMemcpyAsync(&e->d_out->local.sum, &e->h_out->pre4[0], sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    return PAPR_OK;
+}
+
+// finalize + levels, optionally with the exact sequential sum patched in between (two extra passes
+// over the resident shard and two host synchronisations - negligible next to PCIe on the host path)
+static int enqueue_finalize_levels_exact(papr_engine *e, const float *d_iq, u64 n, int graph, bool exact)
+{
+    if (!exact) return enqueue_finalize_levels(e, n, graph);
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
+    e->launches += 1;
+    int rc = apply_exact_sum(e, d_iq, n);
+    if (rc) return rc;
+    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
+                       &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
+    e->launches += 1;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // device-resident analysis
 // ------------------------------------------------------------------------------------------------
 extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n, int graph, papr_result *out)
@@ -540,6 +669,7 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if (mode == PAPR_MODE_AUTO) // fused pays off once the subsample is a small fraction of the shard
         mode = (n >= e->fused_min_samples && stride >= 8) ? PAPR_MODE_FUSED : PAPR_MODE_TWO_PASS;
     out->mode_used = mode;
+    const bool exact = e->exact_sum == 1;
     int rc;
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
@@ -551,11 +681,11 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
         papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
         e->launches += 3;
         if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
-        if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+        if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
         if ((rc = enqueue_resolve(e))) return rc;
     } else {
         if ((rc = enqueue_scan(e, true, false, d_iq, n, 0, true))) return rc;
-        if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+        if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
         if ((rc = enqueue_hist_exact(e, d_iq, n, true))) return rc;
     }
     if ((rc = enqueue_fetch(e))) return rc;
@@ -856,7 +986,7 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
     u64 n = 0;
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = host_stream_stats(e, image, bytes, 0, &n))) return rc;
-    if ((rc = enqueue_finalize_levels(e, n, graph))) return rc;
+    if ((rc = enqueue_finalize_levels_exact(e, e->d_buf, n, graph, e->exact_sum != 0))) return rc;
     if ((rc = enqueue_hist_exact(e, e->d_buf, n, true))) return rc;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));

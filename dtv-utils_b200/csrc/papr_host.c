@@ -176,3 +176,16 @@ float papr_host_stale_q(const unsigned char *img, uint64_t bytes)
     memcpy(&f, q, 4);
     return f;
 }
+
+/* papr.c:103-104 replayed literally on a short run of samples (the tiles of the exact sequential-sum
+ * emulation that may cross a power of two): sum += (I*I)+(Q*Q), float products/sum, double accumulate. */
+double papr_host_seq_add(double sum, const float *iq, uint64_t nsamples)
+{
+    for (uint64_t k = 0; k < nsamples; k++) {
+        volatile float ii = iq[2 * k] * iq[2 * k];
+        volatile float qq = iq[2 * k + 1] * iq[2 * k + 1];
+        volatile float value = ii + qq;
+        sum += value;
+    }
+    return sum;
+}

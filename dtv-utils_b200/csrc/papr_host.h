@@ -10,6 +10,8 @@ extern "C" {
 void papr_host_build_tables(int graph, int n, double *pow10, double *ratio_min);
 /* Q that the reference pairs with a lone trailing I (papr.c:35,101-103) */
 float papr_host_stale_q(const unsigned char *file_image, uint64_t file_bytes);
+/* sum += (double)(I*I+Q*Q) sample by sample, exactly as papr.c:103-104 */
+double papr_host_seq_add(double sum, const float *iq, uint64_t nsamples);
 #ifdef __cplusplus
 }
 #endif

@@ -878,3 +878,132 @@ void papr_launch_find_nan(const float *iq, u64 nsamples, u64 first_index, u64 *o
 {
     papr_find_nan_kernel<<<grid, 256, 0, s>>>(iq, nsamples, first_index, out_idx);
 }
+
+// ------------------------------------------------------------------------------------------------
+// exact emulation of the reference's SEQUENTIAL double sum (papr.c:104)        SURVEY.md §7.3
+// ------------------------------------------------------------------------------------------------
+// sum += (double)value, one sample after the other, rounds to nearest-even at every step; a parallel
+// sum differs from it in the last bits.  Within one binade of the running sum (ulp u = 2^(k-52)) the
+// state is an integer m = sum/u and adding v = (q + f)*u gives m' = m + q + r, where r = 1 iff f > 1/2,
+// or f == 1/2 and m+q is odd - so the effect of a run of samples depends on the entry state only
+// through its PARITY.  A run is therefore a pair (D0, D1): the total increment for an even / odd entry
+// state.  Runs compose associatively (C.Dp = A.Dp + B.D[(p + A.Dp) & 1]), which makes the sequential
+// sum a parallel reduction - exact as long as the running sum stays inside the binade, which the
+// host guarantees per tile from (approximate) prefix sums and re-checks when it chains the tiles.
+// Tiles that may cross a power of two are replayed on the host with real double adds.
+
+// sums of the tiles (only used to place every tile in a binade; any summation order will do)
+__global__ void __launch_bounds__(1024) papr_tilesum_kernel(const float *iq, u64 nsamples, double *tile_sum)
+{
+    __shared__ double s_w[32];
+    const unsigned ntiles = (unsigned)((nsamples + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE);
+    const float4 *p = reinterpret_cast<const float4 *>(iq);
+    for (unsigned t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const u64 s0 = (u64)t * PAPR_SEQ_TILE;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < PAPR_SEQ_TILE / 2 / 1024; ++j) {
+            const u64 s = s0 + 2ull * (threadIdx.x + 1024u * j);
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s + 1 < nsamples) q = ldg_stream(p + (s >> 1));
+            else if (s < nsamples) { float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s); q.x = h.x; q.y = h.y; }
+            acc += (double)power_of(q.x, q.y);
+            acc += (double)power_of(q.z, q.w);
+        }
+        acc = warp_sum_fixed(acc);
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double x = warp_sum_fixed(s_w[threadIdx.x]);
+            if (threadIdx.x == 0) tile_sum[t] = x;
+        }
+        __syncthreads();
+    }
+}
+
+void papr_launch_tilesum(const float *iq, u64 nsamples, double *tile_sum, int grid, cudaStream_t s)
+{
+    papr_tilesum_kernel<<<grid, 1024, 0, s>>>(iq, nsamples, tile_sum);
+}
+
+struct SeqRun { u64 d0, d1; }; // increment (in ulps of the binade) for an even / odd entry state
+
+__device__ __forceinline__ SeqRun seq_compose(const SeqRun &a, const SeqRun &b)
+{
+    SeqRun c;
+    c.d0 = a.d0 + ((a.d0 & 1) ? b.d1 : b.d0);
+    c.d1 = a.d1 + (((1 + a.d1) & 1) ? b.d1 : b.d0);
+    return c;
+}
+
+// one CTA per tile of PAPR_SEQ_TILE samples; thread t owns the 32 consecutive samples t*32..t*32+31
+__global__ void __launch_bounds__(1024) papr_seqsum_kernel(const float *iq, u64 nsamples, const short *tile_code,
+                                                           SeqRun *tile_run)
+{
+    extern __shared__ __align__(16) unsigned char seq_smem[];
+    float *s_v = reinterpret_cast<float *>(seq_smem);      // [1024][33]: row t = the samples of thread t
+    SeqRun *s_run = reinterpret_cast<SeqRun *>(seq_smem);  // reused for the ordered composition
+    const unsigned ntiles = (unsigned)((nsamples + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE);
+    const float4 *p = reinterpret_cast<const float4 *>(iq);
+    const int t = threadIdx.x;
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int k = tile_code[tile];
+        if (k >= PAPR_SEQ_ZERO) continue; // zero or dirty tile: nothing to do here (uniform per CTA)
+        const u64 s0 = (u64)tile * PAPR_SEQ_TILE;
+        for (int j = 0; j < PAPR_SEQ_TILE / 2 / 1024; ++j) {
+            const unsigned f4 = t + 1024u * j;
+            const u64 s = s0 + 2ull * f4;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s + 1 < nsamples) q = ldg_stream(p + (s >> 1));
+            else if (s < nsamples) { float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s); q.x = h.x; q.y = h.y; }
+            const unsigned pos = 2u * f4;
+            float *dst = s_v + (pos >> 5) * 33 + (pos & 31);
+            dst[0] = power_of(q.x, q.y);
+            dst[1] = power_of(q.z, q.w);
+        }
+        __syncthreads();
+        const int U = k - 52; // exponent of the binade's ulp
+        u64 d0 = 0, d1 = 0;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            const unsigned b = __float_as_uint(s_v[t * 33 + i]);
+            if (b == 0) continue;
+            const unsigned e = b >> 23;
+            const unsigned M = e ? ((b & 0x7fffffu) | 0x800000u) : (b & 0x7fffffu); // v = M * 2^E
+            const int E = (int)(e ? e : 1u) - 150;
+            const int shift = U - E;
+            if (shift <= 0) {            // v is a whole number of ulps: exact add
+                const u64 q = (u64)M << (-shift);
+                d0 += q; d1 += q;
+            } else if (shift <= 24) {    // q ulps plus a fraction f = rem / 2^shift
+                const u64 q = M >> shift;
+                const unsigned rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+                u64 r0 = 0, r1 = 0;
+                if (rem > half) { r0 = 1; r1 = 1; }
+                else if (rem == half) { r0 = (d0 + q) & 1; r1 = (1 + d1 + q) & 1; } // tie: to even
+                d0 += q + r0; d1 += q + r1;
+            }                            // shift >= 25: f < 1/2 and q = 0, the add rounds back
+        }
+        __syncthreads();
+        s_run[t].d0 = d0; s_run[t].d1 = d1;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) { // ordered tree: thread t (multiple of 2o) <- t then t+o
+            if ((t & (2 * o - 1)) == 0) s_run[t] = seq_compose(s_run[t], s_run[t + o]);
+            __syncthreads();
+        }
+        if (t == 0) tile_run[tile] = s_run[0];
+        __syncthreads();
+    }
+}
+
+int papr_seqsum_configure(void)
+{
+    return cudaFuncSetAttribute(papr_seqsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4) ==
+                   cudaSuccess ? 0 : -1;
+}
+
+void papr_launch_seqsum(const float *iq, u64 nsamples, const short *tile_code, void *tile_run, int grid,
+                        cudaStream_t s)
+{
+    papr_seqsum_kernel<<<grid, 1024, 1024 * 33 * 4, s>>>(iq, nsamples, tile_code, reinterpret_cast<SeqRun *>(tile_run));
+}

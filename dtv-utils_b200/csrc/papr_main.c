@@ -56,6 +56,7 @@ int papr_main(int argc, char **argv)
     const char *v;
     if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
     if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
+    if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
 
     papr_result *r = (papr_result *)calloc(1, sizeof(*r));
     int rc = papr_analyze_file(e, path, graph, r);

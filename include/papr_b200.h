@@ -91,7 +91,9 @@ const char *papr_last_error(const papr_engine *e); /* e may be NULL: last create
 /* cudaStream_t the engine launches on (for callers that time or order against it). */
 void *papr_engine_stream(papr_engine *e);
 /* Tunables by name ("mode", "presample_stride", "window_sigmas", "chunk_bytes", "staging_threads",
- * "fused_min_samples", "fine_bytes_log2").  Returns PAPR_ERR_ARG for an unknown name. */
+ * "fused_min_samples", "fine_bytes_log2", "exact_sum": -1 (default) = emulate the reference's sequential
+ * double sum (papr.c:104) bit for bit on the file/host path only, 0 = never, 1 = also on the
+ * device-resident path).  Returns PAPR_ERR_ARG for an unknown name. */
 int  papr_engine_set(papr_engine *e, const char *name, double value);
 
 /* ---- the process boundary: replaces main(), papr.c:32-196 ------------------------------------ */
