@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -562,44 +563,67 @@ static int ensure_seq_buffers(papr_engine *e, u64 ntiles)
     return PAPR_OK;
 }
 
-static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double *sum_out)
+// phase 1: sums of this shard's tiles -> e->h_tile_sum (synchronises)
+static int seq_tile_sums(papr_engine *e, const float *d_iq, u64 n)
 {
     const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
-    if (ntiles == 0) { *sum_out = 0.0; return PAPR_OK; }
     int rc;
-    if ((rc = ensure_seq_buffers(e, ntiles))) return rc;
-    // 1. tile sums -> which binade each tile's running sum lives in
+    if ((rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
+    if (ntiles == 0) return PAPR_OK;
     papr_launch_tilesum(d_iq, n, e->d_tile_sum, e->num_sms * 2, e->stream);
     CU(cudaMemcpyAsync(e->h_tile_sum, e->d_tile_sum, ntiles * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    double pre = 0.0;
+    e->launches += 1;
+    return PAPR_OK;
+}
+
+// phase 2 (host): place every tile in a binade, given the running sum `pre` before the shard.
+// Returns 1 if a tile sum is NaN/Inf (the reference's sum is too: nothing to emulate).
+static int seq_classify(const double *tile_sum, u64 ntiles, double *pre_io, short *code)
+{
+    double pre = *pre_io;
     for (u64 t = 0; t < ntiles; ++t) {
-        const double ts = e->h_tile_sum[t];
-        if (!std::isfinite(ts)) return 1; // the reference's sum is NaN/Inf as well: nothing to emulate
-        short code = PAPR_SEQ_DIRTY;
+        const double ts = tile_sum[t];
+        if (!std::isfinite(ts)) return 1;
+        short c = PAPR_SEQ_DIRTY;
         if (ts == 0.0) {
-            code = PAPR_SEQ_ZERO;
+            c = PAPR_SEQ_ZERO;
         } else {
             const double lo = pre * (1.0 - 1e-9), hi = (pre + ts) * (1.0 + 1e-9);
             if (lo > 0.0) {
                 const int k = std::ilogb(lo);
-                if (hi < std::ldexp(1.0, k + 1)) code = (short)k;
+                if (hi < std::ldexp(1.0, k + 1)) c = (short)k;
             }
         }
-        e->h_tile_code[t] = code;
+        code[t] = c;
         pre += ts;
     }
-    // 2. (D0, D1) of every clean tile
+    *pre_io = pre;
+    return 0;
+}
+
+// phase 3: (D0, D1) of every clean tile -> e->h_tile_run (synchronises); codes in e->h_tile_code
+static int seq_tile_runs(papr_engine *e, const float *d_iq, u64 n)
+{
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    if (ntiles == 0) return PAPR_OK;
     CU(cudaMemcpyAsync(e->d_tile_code, e->h_tile_code, ntiles * sizeof(short), cudaMemcpyHostToDevice, e->stream));
     papr_launch_seqsum(d_iq, n, e->d_tile_code, e->d_tile_run, e->num_sms, e->stream);
     CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    e->launches += 2;
+    e->launches += 1;
     e->d2h += ntiles * 24;
     e->h2d += ntiles * 2;
-    // 3. chain the tiles in file order; anything not provably inside its binade is replayed literally
-    double s = 0.0;
-    e->seq_dirty = 0;
+    return PAPR_OK;
+}
+
+// phase 4 (host): chain this shard's tiles onto the running state *s_io in file order; anything not
+// provably inside its binade is replayed literally (D2H of that tile, real double adds)
+static int seq_chain(papr_engine *e, const float *d_iq, u64 n, double *s_io)
+{
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    double s = *s_io;
+    cudaSetDevice(e->device);
     for (u64 t = 0; t < ntiles; ++t) {
         const short code = e->h_tile_code[t];
         if (code == PAPR_SEQ_ZERO) continue;
@@ -621,6 +645,20 @@ static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double
         e->seq_dirty++;
         e->d2h += cnt * 8;
     }
+    *s_io = s;
+    return PAPR_OK;
+}
+
+static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double *sum_out)
+{
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    int rc;
+    double pre = 0.0, s = 0.0;
+    e->seq_dirty = 0;
+    if ((rc = seq_tile_sums(e, d_iq, n))) return rc;
+    if (seq_classify(e->h_tile_sum, ntiles, &pre, e->h_tile_code)) return 1;
+    if ((rc = seq_tile_runs(e, d_iq, n))) return rc;
+    if ((rc = seq_chain(e, d_iq, n, &s))) return rc;
     *sum_out = s;
     return PAPR_OK;
 }
@@ -924,11 +962,12 @@ static int ensure_staging(papr_engine *e)
 
 // Stream the file image into the resident device buffer, running the statistics pass on each chunk
 // as it lands.  On return everything is enqueued; *n_out = samples (incl. the lone-I tail sample).
-static int host_stream_stats(papr_engine *e, const void *image, uint64_t bytes, u64 first, u64 *n_out)
+static int host_stream_stats(papr_engine *e, const void *image, uint64_t bytes, u64 first, u64 *n_out,
+                             const float *tail_override = nullptr)
 {
     const unsigned char *img = (const unsigned char *)image;
     const u64 nfloats = bytes / 4, npairs = nfloats / 2;
-    const bool tail = (nfloats & 1) != 0;
+    const bool tail = tail_override ? true : (nfloats & 1) != 0;
     const u64 n = npairs + (tail ? 1 : 0); // papr.c:102: a lone trailing I still counts as a sample
     *n_out = n;
     int rc;
@@ -941,7 +980,10 @@ static int host_stream_stats(papr_engine *e, const void *image, uint64_t bytes, 
 
     if ((rc = enqueue_reset(e))) return rc;
     float tail_pair[2] = {0.f, 0.f};
-    if (tail) {
+    if (tail_override) {
+        tail_pair[0] = tail_override[0];
+        tail_pair[1] = tail_override[1];
+    } else if (tail) {
         memcpy(&tail_pair[0], img + 4 * (nfloats - 1), 4);
         tail_pair[1] = papr_host_stale_q(img, bytes);
     }
@@ -1038,6 +1080,293 @@ extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, pa
         madvise(img, bytes, MADV_SEQUENTIAL | MADV_WILLNEED);
     }
     int rc = papr_analyze_host(e, img, bytes, graph, out);
+    if (img) munmap(img, bytes);
+    close(fd);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one capture over several GPUs of this box: byte-range shards, one engine + one host thread per GPU,
+// pass-1 states folded in range order on the host (deterministic, first occurrence kept), the exact
+// sequential sum chained across the shards, ONE all-reduce (NCCL over NVLink) of the level counts.
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is dlopen()ed so that single-GPU users do not need it
+
+namespace {
+
+class Barrier {
+public:
+    explicit Barrier(int n) : n_(n), count_(0), gen_(0) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> l(m_);
+        const u64 g = gen_;
+        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(l, [&] { return gen_ != g; });
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_;
+    u64 gen_;
+};
+
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load()
+    {
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) return false;
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return CommInitAll && AllReduce && CommDestroy;
+    }
+};
+
+} // namespace
+
+struct papr_multi {
+    int n = 0;
+    std::vector<int> dev;
+    std::vector<papr_engine *> eng;
+    NcclApi nccl;
+    std::vector<ncclComm_t> comms;
+    std::thread nccl_init;
+    bool nccl_ok = false;
+    std::string nccl_note, err;
+};
+
+extern "C" const char *papr_multi_last_error(const papr_multi *m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+
+extern "C" const char *papr_multi_exchange(const papr_multi *m)
+{
+    return !m ? "" : (m->nccl_ok ? "nccl" : m->nccl_note.c_str());
+}
+
+extern "C" void papr_multi_destroy(papr_multi *m)
+{
+    if (!m) return;
+    if (m->nccl_init.joinable()) m->nccl_init.join();
+    if (m->nccl_ok) for (auto c : m->comms) m->nccl.CommDestroy(c);
+    for (auto e : m->eng) papr_engine_destroy(e);
+    delete m;
+}
+
+extern "C" int papr_multi_create(int ndev, const int *devices, papr_multi **out)
+{
+    if (!out || ndev < 1 || ndev > 64) return PAPR_ERR_ARG;
+    *out = nullptr;
+    papr_multi *m = new papr_multi();
+    m->n = ndev;
+    bool distinct = true;
+    for (int r = 0; r < ndev; ++r) {
+        m->dev.push_back(devices ? devices[r] : r);
+        for (int q = 0; q < r; ++q) distinct &= m->dev[q] != m->dev[r];
+    }
+    // The one exchange of a single-process run is 16 KB of counts that every shard has just copied to
+    // the host anyway, so the default folds them there (deterministic, ~1 us).  PAPR_B200_EXCHANGE=nccl
+    // does it with one ncclAllReduce over NVLink instead; measured here ncclCommInitAll alone costs
+    // 19-54 s (system NCCL 2.27.3, 2 GPUs) against 0.09 s for the whole analysis, hence opt-in.  The
+    // communicator is set up beside engine creation and the first transfers.
+    const char *xch = getenv("PAPR_B200_EXCHANGE");
+    if (!(xch && std::string(xch) == "nccl")) {
+        m->nccl_note = ndev > 1 ? "host" : "none (single shard)";
+    } else if (ndev > 1 && distinct) {
+        m->nccl_init = std::thread([m] {
+            if (!m->nccl.load()) { m->nccl_note = "host (libnccl.so.2 not found)"; return; }
+            m->comms.resize(m->n);
+            ncclResult_t r = m->nccl.CommInitAll(m->comms.data(), m->n, m->dev.data());
+            if (r != ncclSuccess) {
+                m->nccl_note = std::string("host (ncclCommInitAll: ") + (m->nccl.GetErrorString ? m->nccl.GetErrorString(r) : "?") + ")";
+                m->comms.clear();
+                return;
+            }
+            m->nccl_ok = true;
+        });
+    } else {
+        m->nccl_note = ndev > 1 ? "host (virtual shards on one device)" : "none (single shard)";
+    }
+    for (int r = 0; r < ndev; ++r) {
+        papr_engine *e = nullptr;
+        int rc = papr_engine_create(m->dev[r], &e);
+        if (rc != PAPR_OK) {
+            papr_multi_destroy(m);
+            return rc;
+        }
+        m->eng.push_back(e);
+    }
+    *out = m;
+    return PAPR_OK;
+}
+
+extern "C" int papr_multi_set(papr_multi *m, const char *name, double value)
+{
+    if (!m) return PAPR_ERR_ARG;
+    for (auto e : m->eng) {
+        int rc = papr_engine_set(e, name, value);
+        if (rc) { m->err = e->err; return rc; }
+    }
+    return PAPR_OK;
+}
+
+extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_t bytes, int graph, papr_result *out)
+{
+    if (!m || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    graph = graph ? 1 : 0;
+    const int N = m->n;
+    const unsigned char *img = (const unsigned char *)image;
+    const u64 nfloats = bytes / 4, npairs = nfloats / 2;
+    const bool tail = (nfloats & 1) != 0;
+    float tail_pair[2] = {0.f, 0.f};
+    if (tail) {
+        memcpy(&tail_pair[0], img + 4 * (nfloats - 1), 4);
+        tail_pair[1] = papr_host_stale_q(img, bytes); // needs the WHOLE image: the stale Q may sit in another shard
+    }
+    // shard = whole chunks (so chunk, batch and tile boundaries coincide with shard boundaries)
+    const u64 chunk_samples = m->eng[0]->chunk_bytes / 8;
+    u64 per = (npairs + N - 1) / N;
+    per = std::max<u64>(chunk_samples, (per + chunk_samples - 1) / chunk_samples * chunk_samples);
+    const int tail_rank = (int)std::min<u64>((u64)N - 1, npairs / per);
+
+    memset(out, 0, offsetof(papr_result, level));
+    out->mode_used = PAPR_MODE_TWO_PASS;
+    std::vector<papr_stats> st(N);
+    std::vector<u64> ns(N, 0);
+    std::vector<int> rcs(N, PAPR_OK);
+    std::atomic<bool> failed(false);
+    bool exact = m->eng[0]->exact_sum != 0, exact_ok = false, use_nccl = false;
+    papr_stats merged;
+    int L = 0;
+    Barrier bar(N);
+    auto t_begin = std::chrono::steady_clock::now();
+    const bool trace = getenv("PAPR_B200_TRACE") != nullptr;
+    auto mark = [&](int r, const char *what) {
+        if (trace && r == 0)
+            fprintf(stderr, "papr_b200 trace: %-28s %9.3f ms\n", what,
+                    std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
+
+    auto rank_main = [&](int r) {
+        papr_engine *e = m->eng[r];
+        const u64 lo = std::min(npairs, (u64)r * per), hi = std::min(npairs, (u64)(r + 1) * per);
+        auto step = [&](int rc) { if (rc < 0 && !failed.exchange(true)) { rcs[r] = rc; } return rc; };
+        begin_analysis(e);
+        // pass 1 while the shard streams in
+        if (!failed) step(host_stream_stats(e, img + lo * 8, (hi - lo) * 8, lo, &ns[r], (tail && r == tail_rank) ? tail_pair : nullptr));
+        if (!failed) {
+            papr_launch_stats_finalize(e->d_work->wp, e->grid, ns[r], &e->d_out->local, e->stream);
+            cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream);
+            if (cudaStreamSynchronize(e->stream) != cudaSuccess) step(fail(e, PAPR_ERR_CUDA, cudaGetErrorString(cudaGetLastError())));
+            stats_to_host(e->h_out->o.local, &st[r]);
+            if (!failed) step(fix_nan_sign(e, e->d_buf, ns[r], lo, &st[r]));
+        }
+        if (!failed && exact) step(seq_tile_sums(e, e->d_buf, ns[r]));
+        mark(r, "pass 1 + tile sums (rank 0)");
+        bar.wait(); // ---- A: every shard's pass-1 state and tile sums are on the host
+        mark(r, "barrier A");
+        if (r == 0 && !failed) {
+            merged = st[0];
+            for (int q = 1; q < N; ++q) papr_stats_merge(&merged, &st[q]);
+            if (exact && std::isfinite(merged.sum)) {
+                double pre = 0.0;
+                exact_ok = true;
+                for (int q = 0; q < N && exact_ok; ++q) {
+                    const u64 nt = (ns[q] + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+                    if (seq_classify(m->eng[q]->h_tile_sum, nt, &pre, m->eng[q]->h_tile_code)) exact_ok = false;
+                }
+            }
+        }
+        bar.wait(); // ---- B
+        if (!failed && exact_ok) step(seq_tile_runs(e, e->d_buf, ns[r]));
+        bar.wait(); // ---- C: every shard's tile runs are on the host
+        mark(r, "barrier C (tile runs)");
+        if (r == 0 && !failed) {
+            if (exact_ok) {
+                double s = 0.0;
+                for (int q = 0; q < N; ++q)
+                    if (seq_chain(m->eng[q], m->eng[q]->d_buf, ns[q], &s) < 0) { failed = true; rcs[0] = PAPR_ERR_CUDA; }
+                merged.sum = s;
+            }
+            out->stats = merged;
+            L = papr_result_finish(out, graph); // host libm: avg, papr, levels
+            mark(r, "chained sum + host levels");
+            if (m->nccl_init.joinable()) m->nccl_init.join();
+            use_nccl = m->nccl_ok;
+            mark(r, "nccl init joined");
+        }
+        bar.wait(); // ---- D: levels known
+        cudaSetDevice(e->device);
+        if (!failed && L > 0) {
+            int rc = upload_levels(e, out->level, L, merged.peak);
+            if (!rc) rc = enqueue_reset(e);
+            if (!rc) rc = enqueue_hist_exact(e, e->d_buf, ns[r], true);
+            step(rc);
+        }
+        bool nccl_called = false;
+        if (L > 0 && use_nccl) { // every rank must take part, even one that failed locally
+            ncclResult_t nr = m->nccl.AllReduce(e->d_out->counts, e->d_out->counts, PAPR_MAX_LEVELS + 1, ncclUint64, ncclSum,
+                                                m->comms[r], e->stream);
+            nccl_called = nr == ncclSuccess;
+            if (!nccl_called) step(fail(e, PAPR_ERR_CUDA, "ncclAllReduce failed"));
+        }
+        if (L > 0) {
+            enqueue_fetch(e);
+            cudaEventRecord(e->ev_end, e->stream);
+            if (cudaStreamSynchronize(e->stream) != cudaSuccess) step(fail(e, PAPR_ERR_CUDA, "synchronise failed after the CCDF pass"));
+        }
+        mark(r, "CCDF pass + exchange (rank 0)");
+        bar.wait(); // ---- E: counts on the host
+        mark(r, "barrier E");
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < N; ++r) th.emplace_back(rank_main, r);
+    rank_main(0);
+    for (auto &t : th) t.join();
+    if (failed) {
+        for (int r = 0; r < N; ++r)
+            if (rcs[r] < 0) { m->err = "shard " + std::to_string(r) + ": " + m->eng[r]->err; return rcs[r]; }
+        m->err = "shard failure";
+        return PAPR_ERR_CUDA;
+    }
+    u64 miss = 0;
+    for (int j = 0; j < L; ++j) out->level_count[j] = 0;
+    for (int q = 0; q < (use_nccl ? 1 : N) && L > 0; ++q) {
+        const DevOut &o = m->eng[q]->h_out->o;
+        for (int j = 0; j < L; ++j) out->level_count[j] += (int64_t)o.counts[j];
+        miss += o.counts[PAPR_MAX_LEVELS];
+    }
+    if (miss) { m->err = "exact CCDF pass reported a miss"; return PAPR_ERR_INTERNAL; }
+    for (int q = 0; q < N; ++q) {
+        out->kernel_launches += m->eng[q]->launches;
+        out->h2d_bytes += m->eng[q]->h2d;
+        out->d2h_bytes += m->eng[q]->d2h;
+    }
+    out->device_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return PAPR_OK;
+}
+
+extern "C" int papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out)
+{
+    if (!m || !path || !out) return PAPR_ERR_ARG;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { m->err = std::string("cannot open ") + path; return PAPR_ERR_IO; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); m->err = "fstat failed"; return PAPR_ERR_IO; }
+    size_t bytes = (size_t)sb.st_size;
+    void *img = nullptr;
+    if (bytes) {
+        img = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (img == MAP_FAILED) { close(fd); m->err = "mmap failed"; return PAPR_ERR_IO; }
+        madvise(img, bytes, MADV_WILLNEED);
+    }
+    int rc = papr_multi_analyze_host(m, img, bytes, graph, out);
     if (img) munmap(img, bytes);
     close(fd);
     return rc;

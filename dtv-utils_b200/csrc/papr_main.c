@@ -47,34 +47,60 @@ int papr_main(int argc, char **argv)
     }
     fclose(fp);
 
-    papr_engine *e = NULL;
-    const char *dev = getenv("PAPR_B200_DEVICE");
-    if (papr_engine_create(dev ? atoi(dev) : -1, &e) != PAPR_OK) {
-        fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_last_error(NULL));
-        return 1;
-    }
     const char *v;
-    if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
-    if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
-    if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
-
     papr_result *r = (papr_result *)calloc(1, sizeof(*r));
-    int rc = papr_analyze_file(e, path, graph, r);
-    if (rc != PAPR_OK) {
-        fprintf(stderr, "papr: %s\n", papr_last_error(e));
+    int ndev = (v = getenv("PAPR_B200_DEVICES")) ? atoi(v) : 1; /* GPUs to shard the capture over */
+    if (ndev > 1) {
+        papr_multi *m = NULL;
+        /* stdout belongs to the reference's text: keep any NCCL banner / debug output off it */
+        setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+        if (papr_multi_create(ndev, NULL, &m) != PAPR_OK) {
+            fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_multi_last_error(NULL));
+            free(r);
+            return 1;
+        }
+        if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_multi_set(m, "chunk_bytes", atof(v) * 1048576.0);
+        if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_multi_set(m, "staging_threads", atof(v));
+        if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_multi_set(m, "exact_sum", atof(v));
+        int rc = papr_multi_analyze_file(m, path, graph, r);
+        if (rc != PAPR_OK) {
+            fprintf(stderr, "papr: %s\n", papr_multi_last_error(m));
+            papr_multi_destroy(m);
+            free(r);
+            return 1;
+        }
+        if (getenv("PAPR_B200_STATS"))
+            fprintf(stderr, "papr_b200: %d shards, exchange=%s, wall_ms=%.3f launches=%u h2d=%llu\n", ndev,
+                    papr_multi_exchange(m), r->device_ms, r->kernel_launches, (unsigned long long)r->h2d_bytes);
+        papr_multi_destroy(m);
+    } else {
+        papr_engine *e = NULL;
+        const char *dev = getenv("PAPR_B200_DEVICE");
+        if (papr_engine_create(dev ? atoi(dev) : -1, &e) != PAPR_OK) {
+            fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_last_error(NULL));
+            free(r);
+            return 1;
+        }
+        if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
+        if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
+        if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
+        int rc = papr_analyze_file(e, path, graph, r);
+        if (rc != PAPR_OK) {
+            fprintf(stderr, "papr: %s\n", papr_last_error(e));
+            papr_engine_destroy(e);
+            free(r);
+            return 1;
+        }
+        if (getenv("PAPR_B200_STATS"))
+            fprintf(stderr, "papr_b200: device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n", r->device_ms, r->scan_ms,
+                    r->kernel_launches, (unsigned long long)r->h2d_bytes);
         papr_engine_destroy(e);
-        free(r);
-        return 1;
     }
     size_t cap = 256 + (size_t)r->nlevels * 64 + 1024;
     char *text = (char *)malloc(cap);
     long len = papr_format(r, text, cap);
     if (len > 0) fwrite(text, 1, (size_t)len, stdout);
-    if ((v = getenv("PAPR_B200_STATS")))
-        fprintf(stderr, "papr_b200: device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n", r->device_ms, r->scan_ms,
-                r->kernel_launches, (unsigned long long)r->h2d_bytes);
     free(text);
     free(r);
-    papr_engine_destroy(e);
     return 0;
 }

@@ -59,7 +59,9 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_levels", "papr_ccdf_device", "papr_fused_presample", "papr_fused_scan",
                "papr_fused_counts", "papr_format", "papr_result_finish", "papr_siggen_device",
                "papr_engine_device_buffer", "papr_shard_presample_async", "papr_shard_scan_async",
-               "papr_shard_counts_async", "papr_shard_finish"]
+               "papr_shard_counts_async", "papr_shard_finish", "papr_multi_create", "papr_multi_destroy",
+               "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
+               "papr_multi_exchange"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -105,6 +107,16 @@ def load_library(path: Optional[str] = None):
     lib.papr_shard_scan_async.argtypes = [vp, vp, u64, u64, i32, i32]
     lib.papr_shard_counts_async.argtypes = [vp, vp, i32, i32, i32, vp, u64]
     lib.papr_shard_finish.argtypes = [vp, i32, C.POINTER(PaprResult)]
+    lib.papr_multi_create.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]
+    lib.papr_multi_destroy.argtypes = [vp]
+    lib.papr_multi_destroy.restype = None
+    lib.papr_multi_set.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.papr_multi_analyze_host.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
+    lib.papr_multi_analyze_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(PaprResult)]
+    lib.papr_multi_last_error.argtypes = [vp]
+    lib.papr_multi_last_error.restype = C.c_char_p
+    lib.papr_multi_exchange.argtypes = [vp]
+    lib.papr_multi_exchange.restype = C.c_char_p
     if path is None:
         _lib = lib
     return lib
@@ -306,6 +318,60 @@ class Engine:
     def siggen(self, d_out, first_index: int, nsamples: int, seed: int):
         self._check(self.lib.papr_siggen_device(self.h, _ptr(d_out), first_index, nsamples, seed),
                     "papr_siggen_device")
+
+
+class MultiEngine:
+    """One capture sharded by byte range over several GPUs of this box, single process (papr_multi).
+    `devices` may repeat a device index (virtual shards on one GPU; counts are then summed on the host)."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = load_library()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self.lib.papr_multi_create(len(devices), arr, C.byref(h))
+        if rc != 0:
+            raise PaprError(f"papr_multi_create failed ({rc}): {self.lib.papr_multi_last_error(None).decode()}")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.papr_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise PaprError(f"{what} failed ({rc}): {self.lib.papr_multi_last_error(self.h).decode()}")
+
+    def set(self, name: str, value: float):
+        self._check(self.lib.papr_multi_set(self.h, name.encode(), float(value)), "papr_multi_set")
+
+    @property
+    def exchange(self) -> str:
+        return self.lib.papr_multi_exchange(self.h).decode()
+
+    def analyze_host(self, image, nbytes: Optional[int] = None, graph: bool = False) -> PaprResult:
+        keep = None
+        if isinstance(image, (bytes, bytearray)):
+            nbytes = len(image) if nbytes is None else nbytes
+            keep = (C.c_char * max(len(image), 1)).from_buffer_copy(image if image else b"\0")
+            addr = C.addressof(keep)
+        else:
+            if nbytes is None:
+                nbytes = image.numel() * image.element_size() if hasattr(image, "numel") else image.nbytes
+            addr = _ptr(image)
+        res = PaprResult()
+        self._check(self.lib.papr_multi_analyze_host(self.h, addr, nbytes, int(bool(graph)), C.byref(res)),
+                    "papr_multi_analyze_host")
+        del keep
+        return res
+
+    def analyze_file(self, path: str, graph: bool = False) -> PaprResult:
+        res = PaprResult()
+        self._check(self.lib.papr_multi_analyze_file(self.h, os.fsencode(path), int(bool(graph)), C.byref(res)),
+                    "papr_multi_analyze_file")
+        return res
 
 
 # ---- byte-range sharding over ranks (one process per GPU, torch.distributed) -----------------------

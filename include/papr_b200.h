@@ -115,6 +115,23 @@ int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t nsamples, in
 /* Open + mmap + papr_analyze_host. */
 int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out);
 
+/* ---- one capture over several GPUs of this box (single process) --------------------------------- */
+/* Byte-range shards (whole 64 MiB chunks), one engine and one host thread per GPU; pass-1 states
+ * folded in range order, the sequential sum chained across shards, one reduction of the level counts:
+ * on the host by default (they are 16 KB that every shard copies back anyway), or with one
+ * ncclAllReduce over NVLink when PAPR_B200_EXCHANGE=nccl (libnccl.so.2 is dlopen()ed; communicator
+ * setup costs tens of seconds on this pool).  A device may be listed twice
+ * (virtual shards).  devices == NULL means 0..ndev-1. */
+typedef struct papr_multi papr_multi;
+int  papr_multi_create(int ndev, const int *devices, papr_multi **out);
+void papr_multi_destroy(papr_multi *m);
+int  papr_multi_set(papr_multi *m, const char *name, double value);       /* papr_engine_set on every shard */
+int  papr_multi_analyze_host(papr_multi *m, const void *file_image, uint64_t file_bytes, int graph,
+                             papr_result *out);
+int  papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out);
+const char *papr_multi_last_error(const papr_multi *m);
+const char *papr_multi_exchange(const papr_multi *m); /* "nccl" or why the host summed the counts */
+
 /* ---- the stages, for sharded (multi-GPU / multi-process) callers ------------------------------ */
 /* papr.c:100-129 over [first_index, first_index+nsamples) held at d_iq.  Synchronous. */
 int papr_stats_device(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index,

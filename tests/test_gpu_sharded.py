@@ -77,3 +77,49 @@ def test_two_gpus_match_oracle(built, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
+
+
+# ---- single-process multi-GPU driver (papr_multi_*; what `PAPR_B200_DEVICES=N papr` runs) --------------
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("nshards", [2, 3])
+def test_virtual_shards_single_process_all_fixtures(built, manifest, nshards):
+    """N shards on ONE device (devices=[0]*N): range-order merge, shard-boundary tails, the sequential
+    sum chained across shards - stdout identical to the reference on every fixture."""
+    import struct
+    m = built.MultiEngine([0] * nshards)
+    m.set("chunk_bytes", 1 << 20)  # 131072-sample chunks so that even the small fixtures really split
+    assert m.exchange.startswith("host")
+    try:
+        for name in fixtures.FIXTURES:
+            img = fixtures.image(name)
+            if fixtures.md5(img) != manifest[name]["input_md5"]:
+                continue
+            for graph in (False, True):
+                want = open(os.path.join(GOLD, name + (".g.out" if graph else ".out")), "rb").read()
+                res = m.analyze_host(img, graph=graph)
+                assert built.format_result(res) == want, (name, graph)
+        f = fixtures.siggen(0, 900_001, 31)  # sum chained across 3 shards == the oracle's sequential sum
+        st, *_ = oracle_binding.analyze(f, False)
+        res = m.analyze_host(f)
+        assert struct.pack("<d", res.stats.sum) == struct.pack("<d", st.sum)
+    finally:
+        m.close()
+
+
+def test_cli_two_gpus(built, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    f = fixtures.siggen(0, (1 << 24) + 4097, 41)
+    p = tmp_path / "cap.cfile"
+    p.write_bytes(f.tobytes()[:-4])  # odd number of floats: the lone-I tail lands in the last shard
+    for graph, exchange in ((False, "host"), (True, "host"), (False, "nccl")):
+        want = oracle_binding.run_image(p.read_bytes(), graph)
+        env = dict(os.environ, PAPR_B200_DEVICES="2", PAPR_B200_STATS="1", PAPR_B200_CHUNK_MB="16",
+                   PAPR_B200_EXCHANGE=exchange)
+        r = subprocess.run([built.cli_path()] + (["-g"] if graph else []) + [str(p)], capture_output=True, env=env,
+                           timeout=600)
+        assert r.returncode == 0 and r.stdout == want, r.stderr.decode()
+        assert ("exchange=%s" % exchange).encode() in r.stderr, r.stderr
