@@ -164,7 +164,8 @@ def workload_config(args, n):
     return {"workload": "papr %s CCDF on %d GiB synthetic IQ per GPU (BASELINE configs[1] scaled to north_star's >=10 GiB)"
                         % ("-g 0.1 dB-bin" if args.graph else "1 dB-bin", n * 8 >> 30),
             "samples_per_gpu": n, "bytes_per_gpu": n * 8, "graph": bool(args.graph),
-            "generator": "SURVEY Appendix A, seed 1", "l2_policy": "inputs_larger_than_l2 (16 GiB vs 126 MB)",
+            "generator": "SURVEY Appendix A, seed 1" if args.signal == "appendixA" else
+                         "DVB-T2-like 32K OFDM, 256-QAM, GI 1/128, x0.2 (dtv_utils_b200.producers)", "l2_policy": "inputs_larger_than_l2 (16 GiB vs 126 MB)",
             "sharding": "byte-range, one shard per rank"}
 
 
@@ -190,8 +191,12 @@ def run_ours(args):
     eng = pb.Engine(local)
     mode = {"auto": 0, "two_pass": 1, "fused": 2}[args.mode]
     eng.set("mode", mode)
-    d = torch.empty(2 * n, dtype=torch.float32, device="cuda")
-    eng.siggen(d, first, n, 1)
+    if args.signal == "ofdm32k":  # DVB-T2-like 32K OFDM (BASELINE configs[4]); same base block on every rank
+        from dtv_utils_b200.producers import ofdm_capture
+        d = ofdm_capture(n, seed=1 + rank, device="cuda")
+    else:
+        d = torch.empty(2 * n, dtype=torch.float32, device="cuda")
+        eng.siggen(d, first, n, 1)
     torch.cuda.synchronize()
 
     def barrier():
@@ -309,6 +314,9 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                         "samples_per_gpu": n_host, "host_memory": "pinned"},
                 "gpu_launches": launches, "clocks": sampler.result(), "fused_miss": int(res.fused_miss)}
+        if world == 1 and pinned is not None and n_host == n:
+            # the drop-in path (exact sequential sum) and the timed resident path print the same text
+            line["resident_stdout_equals_host_path_stdout"] = bool(pb.format_result(hres) == stdout_resident)
         if world == 1 and not args.no_cpu and pinned is not None:
             line["cpu_baseline"] = cpu_baseline(args, pinned, n_host, graph, eng, pb)
         print(json.dumps(line), flush=True)
@@ -347,6 +355,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2-samples", type=int, default=28)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--signal", default="appendixA", choices=["appendixA", "ofdm32k"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("warmup raised to 3 (timing rules)")

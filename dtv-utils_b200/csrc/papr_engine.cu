@@ -1065,24 +1065,56 @@ extern "C" int papr_stats_host(papr_engine *e, const void *image, uint64_t bytes
     return fix_nan_sign(e, e->d_buf, n, first, out);
 }
 
+// The capture as one host image: mmap for regular files; anything else (FIFO, character device - the
+// reference needs a seekable file, papr.c:142, we do not) is read to the end into memory.
+struct FileImage {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    bool mapped = false;
+    int open(const char *path, std::string &err)
+    {
+        int fd = ::open(path, O_RDONLY);
+        if (fd < 0) { err = std::string("cannot open ") + path; return PAPR_ERR_IO; }
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) { ::close(fd); err = "fstat failed"; return PAPR_ERR_IO; }
+        if (S_ISREG(sb.st_mode)) {
+            bytes = (size_t)sb.st_size;
+            if (bytes) {
+                ptr = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (ptr == MAP_FAILED) { ptr = nullptr; ::close(fd); err = "mmap failed"; return PAPR_ERR_IO; }
+                madvise(ptr, bytes, MADV_WILLNEED);
+                mapped = true;
+            }
+        } else {
+            size_t cap = 1u << 24;
+            char *buf = (char *)malloc(cap);
+            for (;;) {
+                if (!buf) { ::close(fd); err = "out of memory reading the stream"; return PAPR_ERR_IO; }
+                ssize_t got = ::read(fd, buf + bytes, cap - bytes);
+                if (got < 0) { free(buf); ::close(fd); err = "read failed"; return PAPR_ERR_IO; }
+                if (got == 0) break;
+                bytes += (size_t)got;
+                if (bytes == cap) buf = (char *)realloc(buf, cap *= 2);
+            }
+            ptr = buf;
+        }
+        ::close(fd);
+        return PAPR_OK;
+    }
+    ~FileImage()
+    {
+        if (ptr && mapped) munmap(ptr, bytes);
+        else free(ptr);
+    }
+};
+
 extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)
 {
     if (!e || !path || !out) return PAPR_ERR_ARG;
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail(e, PAPR_ERR_IO, std::string("cannot open ") + path);
-    struct stat sb;
-    if (fstat(fd, &sb) != 0) { close(fd); return fail(e, PAPR_ERR_IO, "fstat failed"); }
-    size_t bytes = (size_t)sb.st_size;
-    void *img = nullptr;
-    if (bytes) {
-        img = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (img == MAP_FAILED) { close(fd); return fail(e, PAPR_ERR_IO, "mmap failed"); }
-        madvise(img, bytes, MADV_SEQUENTIAL | MADV_WILLNEED);
-    }
-    int rc = papr_analyze_host(e, img, bytes, graph, out);
-    if (img) munmap(img, bytes);
-    close(fd);
-    return rc;
+    FileImage f;
+    int rc = f.open(path, e->err);
+    if (rc) return rc;
+    return papr_analyze_host(e, f.ptr, f.bytes, graph, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1355,19 +1387,8 @@ extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_
 extern "C" int papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out)
 {
     if (!m || !path || !out) return PAPR_ERR_ARG;
-    int fd = open(path, O_RDONLY);
-    if (fd < 0) { m->err = std::string("cannot open ") + path; return PAPR_ERR_IO; }
-    struct stat sb;
-    if (fstat(fd, &sb) != 0) { close(fd); m->err = "fstat failed"; return PAPR_ERR_IO; }
-    size_t bytes = (size_t)sb.st_size;
-    void *img = nullptr;
-    if (bytes) {
-        img = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (img == MAP_FAILED) { close(fd); m->err = "mmap failed"; return PAPR_ERR_IO; }
-        madvise(img, bytes, MADV_WILLNEED);
-    }
-    int rc = papr_multi_analyze_host(m, img, bytes, graph, out);
-    if (img) munmap(img, bytes);
-    close(fd);
-    return rc;
+    FileImage f;
+    int rc = f.open(path, m->err);
+    if (rc) return rc;
+    return papr_multi_analyze_host(m, f.ptr, f.bytes, graph, out);
 }

@@ -286,3 +286,20 @@ def test_exact_sequential_sum_bit_for_bit(built, eng, torch_cuda):
     finally:
         eng.set("exact_sum", -1)
         eng.set("mode", 0)
+
+
+def test_ofdm_producer_capture_against_oracle(built, eng, torch_cuda):
+    """SURVEY §8f-1 / BASELINE configs[4]: DVB-T2-like 32K OFDM generated on the device."""
+    from dtv_utils_b200.producers import ofdm_capture
+    n = (1 << 22) + 33024 * 3
+    d = ofdm_capture(n, seed=7, device="cuda:0")
+    host = d.cpu().numpy()
+    p = float(np.mean(host.astype(np.float64) ** 2) * 2)
+    assert abs(p - 0.04) < 0.002  # 0.2^2: unit-power constellation through the x0.2 gain (dvbt2-blade.py:132)
+    for graph in (False, True):
+        want = oracle_binding.run_image(host.tobytes(), graph)
+        for mode in (1, 2):
+            eng.set("mode", mode)
+            assert built.format_result(eng.analyze_device(d, n, graph)) == want
+        eng.set("mode", 0)
+        assert built.format_result(eng.analyze_host(host, graph=graph)) == want
