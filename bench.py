@@ -344,6 +344,11 @@ def cpu_baseline(args, pinned, n_host, graph, eng, pb):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's banner / debug output (NCCL_DEBUG=VERSION is set
+    # on some boxes) on stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # this level ignores NCCL_DEBUG_FILE
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

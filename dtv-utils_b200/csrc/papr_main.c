@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 
 #include "../../include/papr_b200.h"
 
@@ -54,6 +55,8 @@ int papr_main(int argc, char **argv)
         papr_multi *m = NULL;
         /* stdout belongs to the reference's text: keep any NCCL banner / debug output off it */
         setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+        if ((v = getenv("NCCL_DEBUG")) && strcasecmp(v, "VERSION") == 0)
+            setenv("NCCL_DEBUG", "WARN", 1); /* the VERSION level ignores NCCL_DEBUG_FILE and prints on stdout */
         if (papr_multi_create(ndev, NULL, &m) != PAPR_OK) {
             fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_multi_last_error(NULL));
             free(r);
