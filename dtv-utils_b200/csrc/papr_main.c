@@ -51,6 +51,16 @@ int papr_main(int argc, char **argv)
     const char *v;
     papr_result *r = (papr_result *)calloc(1, sizeof(*r));
     int ndev = (v = getenv("PAPR_B200_DEVICES")) ? atoi(v) : 1; /* GPUs to shard the capture over */
+    if (ndev < 1) ndev = 1;
+    /* CUDA initialisation time grows with the number of visible GPUs (seconds on an 8-GPU box):
+     * expose only the ones this run uses, unless the user already restricted them */
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        char list[256];
+        int pos = 0, first = (v = getenv("PAPR_B200_DEVICE")) ? atoi(v) : 0;
+        for (int d = 0; d < ndev && pos < 240; d++) pos += snprintf(list + pos, sizeof(list) - pos, d ? ",%d" : "%d", first + d);
+        setenv("CUDA_VISIBLE_DEVICES", list, 1);
+        setenv("PAPR_B200_DEVICE", "0", 1);
+    }
     if (ndev > 1) {
         papr_multi *m = NULL;
         /* stdout belongs to the reference's text: keep any NCCL banner / debug output off it */
