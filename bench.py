@@ -161,11 +161,14 @@ def run_reference_arm(args):
 
 
 def workload_config(args, n):
-    return {"workload": "papr %s CCDF on %d GiB synthetic IQ per GPU (BASELINE configs[1] scaled to north_star's >=10 GiB)"
-                        % ("-g 0.1 dB-bin" if args.graph else "1 dB-bin", n * 8 >> 30),
+    which = "configs[2]" if args.graph else "configs[1] scaled to north_star's >=10 GiB"
+    if args.signal == "ofdm32k":
+        which = "configs[4]"
+    return {"workload": "papr %s CCDF on %d GiB synthetic IQ per GPU (BASELINE %s)"
+                        % ("-g 0.1 dB-bin" if args.graph else "1 dB-bin", n * 8 >> 30, which),
             "samples_per_gpu": n, "bytes_per_gpu": n * 8, "graph": bool(args.graph),
             "generator": "SURVEY Appendix A, seed 1" if args.signal == "appendixA" else
-                         "DVB-T2-like 32K OFDM, 256-QAM, GI 1/128, x0.2 (dtv_utils_b200.producers)", "l2_policy": "inputs_larger_than_l2 (16 GiB vs 126 MB)",
+                         "DVB-T2-like 32K OFDM, 256-QAM, GI 1/128, x0.2 (dtv_utils_b200.producers)", "l2_policy": "inputs_larger_than_l2 (%d GiB vs 126 MB)" % (n * 8 >> 30),
             "sharding": "byte-range, one shard per rank"}
 
 
