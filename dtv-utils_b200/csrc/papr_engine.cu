@@ -1026,13 +1026,24 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
     out->mode_used = PAPR_MODE_TWO_PASS;
     int rc;
     u64 n = 0;
+    const bool trace = getenv("PAPR_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "papr_b200 trace: %-34s %9.3f ms\n", what,
+                    std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = host_stream_stats(e, image, bytes, 0, &n))) return rc;
+    mark("buffers + staging + H2D enqueued");
+    if (trace) { CU(cudaStreamSynchronize(e->stream)); mark("H2D + pass 1 complete"); }
     if ((rc = enqueue_finalize_levels_exact(e, e->d_buf, n, graph, e->exact_sum != 0))) return rc;
+    mark("finalize (+ exact sum)");
     if ((rc = enqueue_hist_exact(e, e->d_buf, n, true))) return rc;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    mark("CCDF pass + fetch");
     stats_to_host(e->h_out->o.merged, &out->stats);
     if ((rc = fix_nan_sign(e, e->d_buf, n, 0, &out->stats))) return rc;
     if (collect(e, graph, out, true)) {

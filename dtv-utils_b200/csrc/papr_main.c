@@ -8,8 +8,16 @@
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <time.h>
 
 #include "../../include/papr_b200.h"
+
+static double now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 static void usage(void)
 {
@@ -89,6 +97,7 @@ int papr_main(int argc, char **argv)
     } else {
         papr_engine *e = NULL;
         const char *dev = getenv("PAPR_B200_DEVICE");
+        const double t0 = now_ms();
         if (papr_engine_create(dev ? atoi(dev) : -1, &e) != PAPR_OK) {
             fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_last_error(NULL));
             free(r);
@@ -97,7 +106,9 @@ int papr_main(int argc, char **argv)
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
         if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
+        const double t1 = now_ms();
         int rc = papr_analyze_file(e, path, graph, r);
+        const double t2 = now_ms();
         if (rc != PAPR_OK) {
             fprintf(stderr, "papr: %s\n", papr_last_error(e));
             papr_engine_destroy(e);
@@ -105,8 +116,8 @@ int papr_main(int argc, char **argv)
             return 1;
         }
         if (getenv("PAPR_B200_STATS"))
-            fprintf(stderr, "papr_b200: device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n", r->device_ms, r->scan_ms,
-                    r->kernel_launches, (unsigned long long)r->h2d_bytes);
+            fprintf(stderr, "papr_b200: create_ms=%.1f analyze_ms=%.1f device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n",
+                    t1 - t0, t2 - t1, r->device_ms, r->scan_ms, r->kernel_launches, (unsigned long long)r->h2d_bytes);
         papr_engine_destroy(e);
     }
     size_t cap = 256 + (size_t)r->nlevels * 64 + 1024;
