@@ -22,6 +22,7 @@
 #include <thread>
 #include <vector>
 
+#include <errno.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -34,7 +35,12 @@ typedef unsigned long long u64;
 
 namespace {
 
-constexpr int kStages = 3;                 // pinned staging buffers for pageable sources
+constexpr int kStages = 4;                 // pinned staging buffers for pageable / file sources
+constexpr int kRing = 4;                   // device chunk buffers of the re-streaming (capture > HBM) mode
+constexpr int kSeqLagRing = 3;             // chunks between a chunk's tile sums and its tile runs (< kRing) ...
+constexpr int kSeqLagResident = 6;         // ... and when nothing limits how far the copies run ahead (< kSeqEvents)
+constexpr int kSeqEvents = 8;
+constexpr size_t kTileBytes = (size_t)PAPR_SEQ_TILE * 8; // chunks are whole tiles of the exact-sum emulation
 constexpr u64 kMaxLaunchSamples = 1ull << 31;  // per scan launch (32-bit sample offsets inside a launch)
 constexpr int kLevels1dB = 256;            // table sizes: PAPR < 192.7 dB (papr_b200.h)
 constexpr int kLevelsGraph = PAPR_MAX_LEVELS;
@@ -67,9 +73,11 @@ struct HostOut {
 
 std::string g_create_error;
 
-// fork-join helper threads for staging pageable captures into pinned memory
+// fork-join helper threads that fill a pinned staging buffer from a pageable image (memcpy) or a
+// file (pread), each worker one page-aligned slice of the chunk
 class CopyPool {
 public:
+    typedef std::function<bool(size_t lo, size_t hi)> SliceFn;
     explicit CopyPool(int n) : stop_(false), pending_(0), gen_(0)
     {
         for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
@@ -83,19 +91,20 @@ public:
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
-    int size() const { return (int)workers_.size(); }
-    void copy(void *dst, const void *src, size_t bytes)
+    // fn(lo, hi) for disjoint slices covering [0, bytes); false if any slice failed
+    bool parallel(size_t bytes, const SliceFn &fn)
     {
-        if (workers_.empty() || bytes < (1u << 20)) { memcpy(dst, src, bytes); return; }
+        if (workers_.empty() || bytes < (1u << 20)) return fn(0, bytes);
         {
             std::lock_guard<std::mutex> l(m_);
-            dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes;
+            fn_ = &fn; bytes_ = bytes; ok_ = true;
             pending_ = (int)workers_.size();
             ++gen_;
         }
         cv_.notify_all();
         std::unique_lock<std::mutex> l(m_);
         done_.wait(l, [this] { return pending_ == 0; });
+        return ok_;
     }
 
 private:
@@ -109,20 +118,52 @@ private:
             seen = gen_;
             size_t n = workers_.size(), per = (bytes_ / n + 4095) & ~(size_t)4095;
             size_t lo = std::min(bytes_, per * id), hi = std::min(bytes_, lo + per);
-            char *d = dst_; const char *s = src_;
+            const SliceFn *fn = fn_;
             l.unlock();
-            if (hi > lo) memcpy(d + lo, s + lo, hi - lo);
+            bool ok = hi > lo ? (*fn)(lo, hi) : true;
             l.lock();
+            if (!ok) ok_ = false;
             if (--pending_ == 0) done_.notify_all();
         }
     }
     std::vector<std::thread> workers_;
     std::mutex m_;
     std::condition_variable cv_, done_;
-    bool stop_;
+    bool stop_, ok_ = true;
     int pending_;
     u64 gen_;
-    char *dst_ = nullptr; const char *src_ = nullptr; size_t bytes_ = 0;
+    const SliceFn *fn_ = nullptr;
+    size_t bytes_ = 0;
+};
+
+// where the capture's bytes come from: a memory image (pinned or pageable) or a regular file, read
+// with pread() straight into the pinned staging buffers (no page faults, no mapping to tear down)
+struct HostSource {
+    const unsigned char *img = nullptr;
+    int fd = -1;
+    u64 base = 0;  // file offset of byte 0 of this source (shards of one file)
+    u64 bytes = 0;
+    bool pinned = false;
+    HostSource slice(u64 off, u64 len) const
+    {
+        HostSource s = *this;
+        if (s.img) s.img += off; else s.base += off;
+        s.bytes = len;
+        return s;
+    }
+    bool read(void *dst, u64 off, size_t len) const
+    {
+        if (img) { memcpy(dst, img + off, len); return true; }
+        off += base;
+        char *d = (char *)dst;
+        while (len) {
+            ssize_t got = pread(fd, d, len, (off_t)off);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) return false; // I/O error, or the file shrank under us
+            d += got; off += (u64)got; len -= (size_t)got;
+        }
+        return true;
+    }
 };
 
 } // namespace
@@ -135,8 +176,8 @@ struct papr_engine {
     int mode = PAPR_MODE_AUTO;
     int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
-    size_t chunk_bytes = 64u << 20;
-    int staging_threads = 8;
+    size_t chunk_bytes = 16u << 20; // measured on the file path: 16 MiB chunks stay in the host LLC
+    int staging_threads = -1;       // -1: min(16, hardware threads)
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
@@ -161,11 +202,18 @@ struct papr_engine {
     // host path
     float *d_buf = nullptr;
     size_t d_buf_bytes = 0;
-    void *h_stage[kStages] = {nullptr, nullptr, nullptr};
+    void *h_stage[kStages] = {};
     size_t h_stage_bytes = 0;
-    cudaEvent_t stage_done[kStages] = {nullptr, nullptr, nullptr};
+    cudaEvent_t stage_done[kStages] = {};
     cudaEvent_t chunk_ready = nullptr;
     CopyPool *pool = nullptr;
+    // re-streaming mode (capture larger than the resident budget): ring of device chunk buffers
+    float *d_ring = nullptr;
+    size_t d_ring_chunk = 0;
+    cudaEvent_t ring_free[kRing] = {};
+    cudaEvent_t seq_ev[kSeqEvents] = {};
+    u64 max_resident_bytes = 0; // 0 = whatever cudaMemGetInfo leaves after a 1 GiB reserve
+    bool streamed = false;      // the last host-path analysis ran in re-streaming mode
     // timing / accounting
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_scan[4] = {nullptr, nullptr, nullptr, nullptr};
     int scan_pairs = 0;
@@ -246,6 +294,8 @@ static int engine_init(papr_engine *e, int device)
     CU(cudaEventCreate(&e->ev_end));
     for (auto &ev : e->ev_scan) CU(cudaEventCreate(&ev));
     for (auto &ev : e->stage_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->ring_free) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &ev : e->seq_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&e->chunk_ready, cudaEventDisableTiming));
     return PAPR_OK;
 }
@@ -280,6 +330,9 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (e->h_out) cudaFreeHost(e->h_out);
     for (auto &p : e->h_stage) if (p) cudaFreeHost(p);
     for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ring_free) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->seq_ev) if (ev) cudaEventDestroy(ev);
+    cudaFree(e->d_ring);
     for (auto &ev : e->ev_scan) if (ev) cudaEventDestroy(ev);
     if (e->chunk_ready) cudaEventDestroy(e->chunk_ready);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -296,8 +349,9 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     if (n == "mode") e->mode = (int)v;
     else if (n == "presample_stride") e->presample_stride = std::max(1, (int)v);
     else if (n == "window_sigmas") e->window_sigmas = (float)v;
-    else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(size_t)((PAPR_BATCH_SAMPLES * 8) - 1));
-    else if (n == "staging_threads") { e->staging_threads = std::max(0, (int)v); delete e->pool; e->pool = nullptr; }
+    else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(kTileBytes - 1));
+    else if (n == "staging_threads") { e->staging_threads = std::max(-1, (int)v); delete e->pool; e->pool = nullptr; }
+    else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
     else if (n == "exact_sum") e->exact_sum = (int)v;
     else if (n == "fine_bytes_log2") e->fine_bytes_log2 = std::min(26, std::max(4, (int)v)); // <= the allocation
@@ -367,23 +421,44 @@ static int enqueue_resolve(papr_engine *e)
     return PAPR_OK;
 }
 
-// exact-threshold CCDF pass over resident data (d_out->lv / d_out->merged already hold levels and peak)
-static int enqueue_hist_exact(papr_engine *e, const float *d_iq, u64 n, bool timed)
+// exact-threshold CCDF pass (d_out->lv / d_out->merged already hold levels and peak), in three steps so
+// that the middle one can run per chunk when the capture is re-streamed instead of resident
+static int hist_begin(papr_engine *e)
 {
     papr_launch_plan_exact(&e->d_out->lv, &e->d_out->merged, e->fine_bytes_log2, &e->d_out->plan, e->d_fine_base,
                            e->stream);
     papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 2;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+static int hist_chunk(papr_engine *e, const float *d_iq, u64 n, bool timed)
+{
     int rc = enqueue_scan(e, false, true, d_iq, n, 0, timed);
     if (rc) return rc;
     papr_launch_bsearch(d_iq, n, &e->d_out->plan, &e->d_out->lv, e->d_work->bhist, e->grid, e->stream); // no-op unless PLAN_BSEARCH
     e->launches += 1;
-    rc = enqueue_resolve(e);
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+static int hist_end(papr_engine *e)
+{
+    int rc = enqueue_resolve(e);
     if (rc) return rc;
     papr_launch_bsearch_counts(&e->d_out->plan, &e->d_out->lv, e->d_work->bhist, e->d_out->counts, e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
+}
+
+static int enqueue_hist_exact(papr_engine *e, const float *d_iq, u64 n, bool timed)
+{
+    int rc;
+    if ((rc = hist_begin(e))) return rc;
+    if ((rc = hist_chunk(e, d_iq, n, timed))) return rc;
+    return hist_end(e);
 }
 
 static int enqueue_fetch(papr_engine *e)
@@ -618,35 +693,51 @@ static int seq_tile_runs(papr_engine *e, const float *d_iq, u64 n)
 }
 
 // phase 4 (host): chain this shard's tiles onto the running state *s_io in file order; anything not
-// provably inside its binade is replayed literally (D2H of that tile, real double adds)
-static int seq_chain(papr_engine *e, const float *d_iq, u64 n, double *s_io)
+// provably inside its binade is replayed literally (real double adds on the tile's samples, which
+// `fetch` brings to e->h_tile_data: a D2H copy for resident shards, a host read when re-streaming)
+typedef std::function<int(u64 first, u64 cnt, float *dst)> TileFetch;
+
+static int seq_chain(papr_engine *e, u64 n, double *s_io, const TileFetch &fetch)
 {
     const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    const u64 mant = (1ull << 52) - 1;
     double s = *s_io;
-    cudaSetDevice(e->device);
     for (u64 t = 0; t < ntiles; ++t) {
         const short code = e->h_tile_code[t];
         if (code == PAPR_SEQ_ZERO) continue;
         if (code != PAPR_SEQ_DIRTY) {
-            const int k = code;
-            if (s >= std::ldexp(1.0, k) && s < std::ldexp(1.0, k + 1)) {
-                const u64 m = (u64)std::ldexp(s, 52 - k); // exact: s is a multiple of 2^(k-52)
+            u64 bits;
+            memcpy(&bits, &s, 8);
+            const unsigned ef = (unsigned)(bits >> 52); // sign + exponent field; s in [2^k, 2^(k+1)) <=> ef == k + 1023
+            if (ef != 0 && ef == (unsigned)((int)code + 1023)) {
+                const u64 m = (bits & mant) | (1ull << 52); // s = m * 2^(k-52), exactly
                 const u64 m2 = m + ((m & 1) ? e->h_tile_run[2 * t + 1] : e->h_tile_run[2 * t]);
-                if (m2 < (1ull << 53)) {
-                    s = std::ldexp((double)m2, k - 52);
+                if (m2 < (1ull << 53)) { // still inside the binade: the tile's run applies as computed
+                    bits = ((u64)ef << 52) | (m2 & mant);
+                    memcpy(&s, &bits, 8);
                     continue;
                 }
             }
         }
         const u64 first = t * PAPR_SEQ_TILE, cnt = std::min<u64>(PAPR_SEQ_TILE, n - first);
-        CU(cudaMemcpyAsync(e->h_tile_data, d_iq + 2 * first, cnt * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        int rc = fetch(first, cnt, e->h_tile_data);
+        if (rc) return rc;
         s = papr_host_seq_add(s, e->h_tile_data, cnt);
         e->seq_dirty++;
-        e->d2h += cnt * 8;
     }
     *s_io = s;
     return PAPR_OK;
+}
+
+static int seq_chain_resident(papr_engine *e, const float *d_iq, u64 n, double *s_io)
+{
+    cudaSetDevice(e->device);
+    return seq_chain(e, n, s_io, [&](u64 first, u64 cnt, float *dst) -> int {
+        CU(cudaMemcpyAsync(dst, d_iq + 2 * first, cnt * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->d2h += cnt * 8;
+        return PAPR_OK;
+    });
 }
 
 static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double *sum_out)
@@ -658,7 +749,7 @@ static int exact_sequential_sum(papr_engine *e, const float *d_iq, u64 n, double
     if ((rc = seq_tile_sums(e, d_iq, n))) return rc;
     if (seq_classify(e->h_tile_sum, ntiles, &pre, e->h_tile_code)) return 1;
     if ((rc = seq_tile_runs(e, d_iq, n))) return rc;
-    if ((rc = seq_chain(e, d_iq, n, &s))) return rc;
+    if ((rc = seq_chain_resident(e, d_iq, n, &s))) return rc;
     *sum_out = s;
     return PAPR_OK;
 }
@@ -674,6 +765,41 @@ static int apply_exact_sum(papr_engine *e, const float *d_iq, u64 n)
         CU(cudaMemcpyAsync(&e->d_out->local.sum, &e->h_out->pre4[0], sizeof(double), cudaMemcpyHostToDevice, e->stream));
     }
     return PAPR_OK;
+}
+
+// The same four phases as stages, for a capture sharded over processes (one rank per GPU): every rank
+// prepares and computes its runs in parallel; only the chaining walks the ranks in index order.
+extern "C" int papr_seqsum_prepare(papr_engine *e, const float *d_iq, uint64_t n, double *approx)
+{
+    if (!e || !approx || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    cudaSetDevice(e->device);
+    int rc = seq_tile_sums(e, d_iq, n);
+    if (rc) return rc;
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    double s = 0.0;
+    for (u64 t = 0; t < ntiles; ++t) s += e->h_tile_sum[t];
+    *approx = s;
+    return PAPR_OK;
+}
+
+extern "C" int papr_seqsum_runs(papr_engine *e, const float *d_iq, uint64_t n, double pre)
+{
+    if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    if (ntiles > e->seq_tiles) return fail(e, PAPR_ERR_ARG, "papr_seqsum_prepare must run first");
+    cudaSetDevice(e->device);
+    if (!std::isfinite(pre) || seq_classify(e->h_tile_sum, ntiles, &pre, e->h_tile_code)) return 1;
+    return seq_tile_runs(e, d_iq, n);
+}
+
+extern "C" int papr_seqsum_chain(papr_engine *e, const float *d_iq, uint64_t n, double *state)
+{
+    if (!e || !state || (n && !d_iq)) return PAPR_ERR_ARG;
+    const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    if (ntiles > e->seq_tiles) return fail(e, PAPR_ERR_ARG, "papr_seqsum_runs must run first");
+    e->seq_dirty = 0;
+    return seq_chain_resident(e, d_iq, n, state);
 }
 
 // finalize + levels, optionally with the exact sequential sum patched in between (two extra passes
@@ -935,9 +1061,12 @@ extern "C" int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// host-buffer analysis: chunked H2D (direct from pinned sources, through a pinned staging ring filled
-// by helper threads for pageable ones), statistics pass per chunk as it lands, shard kept resident
-// in HBM so the CCDF pass never touches PCIe again.
+// host-side captures: chunked H2D (direct from pinned sources; through a pinned staging ring filled by
+// helper threads with memcpy / pread for pageable images and files), the statistics pass - and, chunk
+// by chunk, the exact sequential-sum emulation - running on each chunk as it lands, so that only the
+// CCDF pass is left when the last byte has crossed PCIe.  The shard stays resident in HBM for that
+// pass; a capture larger than the resident budget is streamed a second time instead, through a ring
+// of device chunk buffers (the reference reads its file twice as well, papr.c:142).
 // ------------------------------------------------------------------------------------------------
 static int ensure_device_buffer(papr_engine *e, size_t bytes)
 {
@@ -949,6 +1078,16 @@ static int ensure_device_buffer(papr_engine *e, size_t bytes)
     return PAPR_OK;
 }
 
+static int ensure_ring(papr_engine *e)
+{
+    if (e->d_ring && e->d_ring_chunk == e->chunk_bytes) return PAPR_OK;
+    if (e->d_ring) { cudaFree(e->d_ring); e->d_ring = nullptr; }
+    if (e->d_buf) { cudaFree(e->d_buf); e->d_buf = nullptr; e->d_buf_bytes = 0; } // make room
+    CU(cudaMalloc(&e->d_ring, (size_t)kRing * e->chunk_bytes + 16));
+    e->d_ring_chunk = e->chunk_bytes;
+    return PAPR_OK;
+}
+
 static int ensure_staging(papr_engine *e)
 {
     if (e->h_stage_bytes != e->chunk_bytes) {
@@ -956,76 +1095,267 @@ static int ensure_staging(papr_engine *e)
         for (auto &p : e->h_stage) CU(cudaHostAlloc(&p, e->chunk_bytes, cudaHostAllocDefault));
         e->h_stage_bytes = e->chunk_bytes;
     }
-    if (!e->pool) e->pool = new CopyPool(e->staging_threads);
+    if (!e->pool) {
+        int n = e->staging_threads;
+        if (n < 0) n = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        e->pool = new CopyPool(n);
+    }
     return PAPR_OK;
 }
 
-// Stream the file image into the resident device buffer, running the statistics pass on each chunk
-// as it lands.  On return everything is enqueued; *n_out = samples (incl. the lone-I tail sample).
-static int host_stream_stats(papr_engine *e, const void *image, uint64_t bytes, u64 first, u64 *n_out,
-                             const float *tail_override = nullptr)
+// does a shard of `bytes` stay resident?  (tunable "max_resident_bytes"; default: what the device has
+// free right now - counting the buffer this engine already holds - minus a 1 GiB reserve)
+static bool fits_resident(papr_engine *e, u64 bytes)
 {
-    const unsigned char *img = (const unsigned char *)image;
-    const u64 nfloats = bytes / 4, npairs = nfloats / 2;
-    const bool tail = tail_override ? true : (nfloats & 1) != 0;
-    const u64 n = npairs + (tail ? 1 : 0); // papr.c:102: a lone trailing I still counts as a sample
-    *n_out = n;
-    int rc;
-    if ((rc = ensure_device_buffer(e, n * 8 + 16))) return rc;
+    if (e->max_resident_bytes) return bytes <= e->max_resident_bytes;
+    if (bytes <= e->d_buf_bytes) return true;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return true; }
+    const u64 avail = (u64)free_b + e->d_buf_bytes;
+    return bytes + (1ull << 30) <= avail;
+}
 
-    cudaPointerAttributes attr;
-    bool pinned = bytes && cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (!pinned && npairs && (rc = ensure_staging(e))) return rc;
-
-    if ((rc = enqueue_reset(e))) return rc;
+// geometry of one host-side shard
+struct StreamGeom {
+    u64 npairs = 0, n = 0;     // complete pairs in the source; samples incl. the lone-I tail sample
+    bool tail = false;
     float tail_pair[2] = {0.f, 0.f};
+    u64 chunk_samples = 0, first = 0;
+};
+
+// The lone trailing I of a capture with an odd number of floats is paired with a stale Q
+// (papr_host_stale_q explains which); same rule, reading through the source
+static float stale_q_of(const HostSource &src)
+{
+    if (src.img) return papr_host_stale_q(src.img, src.bytes);
+    const u64 chunk = 16384, nfloats = src.bytes / 4, last = nfloats - 1; // CHUNK_SIZE, papr.c:30
+    const u64 slot = last % chunk + 1, chunk_start = last - last % chunk;
+    unsigned char q[4] = {0, 0, 0, 0};
+    float f;
+    if (chunk_start >= chunk) src.read(q, 4 * (chunk_start - chunk + slot), 4);
+    if (src.bytes % 4) src.read(q, 4 * nfloats, src.bytes % 4);
+    memcpy(&f, q, 4);
+    return f;
+}
+
+static int make_geom(papr_engine *e, const HostSource &src, u64 first, const float *tail_override, StreamGeom *g)
+{
+    const u64 nfloats = src.bytes / 4;
+    g->npairs = nfloats / 2;
+    g->tail = tail_override ? true : (nfloats & 1) != 0;
+    g->n = g->npairs + (g->tail ? 1 : 0); // papr.c:102: a lone trailing I still counts as a sample
+    g->first = first;
+    g->chunk_samples = e->chunk_bytes / 8;
     if (tail_override) {
-        tail_pair[0] = tail_override[0];
-        tail_pair[1] = tail_override[1];
-    } else if (tail) {
-        memcpy(&tail_pair[0], img + 4 * (nfloats - 1), 4);
-        tail_pair[1] = papr_host_stale_q(img, bytes);
+        g->tail_pair[0] = tail_override[0];
+        g->tail_pair[1] = tail_override[1];
+    } else if (g->tail) {
+        if (!src.read(&g->tail_pair[0], 4 * (nfloats - 1), 4)) return fail(e, PAPR_ERR_IO, "read failed");
+        g->tail_pair[1] = stale_q_of(src);
     }
-    const u64 chunk_samples = e->chunk_bytes / 8;
-    int stage = 0;
-    for (u64 off = 0; off < n; off += chunk_samples) {
-        const u64 m = std::min(chunk_samples, n - off);              // samples of this chunk (incl. the tail sample)
-        const u64 mp = std::min(m, npairs > off ? npairs - off : 0); // complete pairs to copy from the image
+    return PAPR_OK;
+}
+
+// One PCIe pass: chunk c = samples [off, off+m) lands at d_chunk, then work(d_chunk, off, m, c, last)
+// enqueues on e->stream.  Re-streaming: work must call release(c') (recorded on e->stream) once
+// everything that reads chunk c' is enqueued; its ring slot is refilled only after that.
+typedef std::function<void(u64 c)> ChunkRelease;
+typedef std::function<int(const float *d_chunk, u64 off, u64 m, u64 c, bool last, const ChunkRelease &release)> ChunkWork;
+
+static int stream_chunks(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, const ChunkWork &work)
+{
+    int stage = 0, rc;
+    const ChunkRelease release = [&](u64 c) {
+        if (!resident) cudaEventRecord(e->ring_free[c % kRing], e->stream);
+    };
+    u64 c = 0;
+    for (u64 off = 0; off < g.n; off += g.chunk_samples, ++c) {
+        const u64 m = std::min(g.chunk_samples, g.n - off);               // samples of this chunk (incl. the tail sample)
+        const u64 mp = std::min(m, g.npairs > off ? g.npairs - off : 0);  // complete pairs to copy from the source
+        float *dst = resident ? e->d_buf + 2 * off : e->d_ring + (c % kRing) * (e->d_ring_chunk / 4);
+        if (!resident) CU(cudaStreamWaitEvent(e->copy_stream, e->ring_free[c % kRing], 0)); // previous tenant consumed?
         if (mp) {
-            const void *src = img + off * 8;
-            if (!pinned) {
-                CU(cudaEventSynchronize(e->stage_done[stage])); // ring slot free again?
-                e->pool->copy(e->h_stage[stage], src, mp * 8);
-                src = e->h_stage[stage];
+            const void *from;
+            if (src.pinned) {
+                from = src.img + off * 8;
+            } else {
+                CU(cudaEventSynchronize(e->stage_done[stage])); // staging slot free again?
+                char *sb = (char *)e->h_stage[stage];
+                const u64 base = off * 8;
+                const bool ok = e->pool->parallel(mp * 8, [&](size_t lo, size_t hi) { return src.read(sb + lo, base + lo, hi - lo); });
+                if (!ok) return fail(e, PAPR_ERR_IO, "read failed while streaming the capture");
+                from = sb;
             }
-            CU(cudaMemcpyAsync(e->d_buf + 2 * off, src, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
-            if (!pinned) {
+            CU(cudaMemcpyAsync(dst, from, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
+            if (!src.pinned) {
                 CU(cudaEventRecord(e->stage_done[stage], e->copy_stream));
                 stage = (stage + 1) % kStages;
             }
             e->h2d += mp * 8;
         }
-        if (tail && off + m == n) {
-            CU(cudaMemcpyAsync(e->d_buf + 2 * npairs, tail_pair, 8, cudaMemcpyHostToDevice, e->copy_stream));
+        if (g.tail && off + m == g.n) {
+            CU(cudaMemcpyAsync(dst + 2 * (g.npairs - off), g.tail_pair, 8, cudaMemcpyHostToDevice, e->copy_stream));
             e->h2d += 8;
         }
         CU(cudaEventRecord(e->chunk_ready, e->copy_stream));
         CU(cudaStreamWaitEvent(e->stream, e->chunk_ready, 0));
-        if ((rc = enqueue_scan(e, true, false, e->d_buf + 2 * off, m, first + off, false))) return rc;
+        if ((rc = work(dst, off, m, c, off + m == g.n, release))) return rc;
     }
     return PAPR_OK;
 }
 
-extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t bytes, int graph, papr_result *out)
+// brings a tile's samples to the host for a literal replay (seq_chain): D2H when the shard is
+// resident, otherwise a read from the source (+ the synthesised tail pair)
+static TileFetch tile_fetcher(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident)
 {
-    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    return [e, &src, &g, resident](u64 first, u64 cnt, float *dst) -> int {
+        if (resident) {
+            CU(cudaMemcpyAsync(dst, e->d_buf + 2 * first, cnt * 8, cudaMemcpyDeviceToHost, e->stream));
+            CU(cudaStreamSynchronize(e->stream));
+            e->d2h += cnt * 8;
+            return PAPR_OK;
+        }
+        const u64 pairs = std::min(cnt, g.npairs > first ? g.npairs - first : 0);
+        if (pairs && !src.read(dst, first * 8, pairs * 8)) return fail(e, PAPR_ERR_IO, "read failed while replaying a tile");
+        if (pairs < cnt) { dst[2 * pairs] = g.tail_pair[0]; dst[2 * pairs + 1] = g.tail_pair[1]; }
+        return PAPR_OK;
+    };
+}
+
+// Pass 1 over a host-side shard: statistics per chunk as it lands; with inline_exact also the exact
+// sequential sum (tile sums per chunk, tiles placed in binades kSeqLag chunks later, tile runs on the
+// GPU while later chunks are still crossing PCIe; the host chains them at the end).  On return the
+// local state is finalized in d_out->local (sum already exact if *exact_done) - nothing synchronised
+// unless inline_exact.
+static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, bool inline_exact,
+                      bool *exact_done)
+{
+    int rc;
+    *exact_done = false;
+    const u64 ntiles = (g.n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+    if (inline_exact && (rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
+    if ((rc = enqueue_reset(e))) return rc;
+
+    struct Pending { const float *d; u64 off, m, c; };
+    std::vector<Pending> pend;
+    size_t pend_head = 0;
+    bool seq_ok = inline_exact;
+    double pre = 0.0;
+    e->seq_dirty = 0;
+    auto process = [&](const Pending &ch, const ChunkRelease &release) -> int {
+        const u64 tile0 = ch.off / PAPR_SEQ_TILE, nt = (ch.m + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+        CU(cudaEventSynchronize(e->seq_ev[ch.c % kSeqEvents])); // this chunk's tile sums are on the host
+        if (seq_ok && seq_classify(e->h_tile_sum + tile0, nt, &pre, e->h_tile_code + tile0)) seq_ok = false;
+        if (seq_ok) {
+            CU(cudaMemcpyAsync(e->d_tile_code + tile0, e->h_tile_code + tile0, nt * sizeof(short), cudaMemcpyHostToDevice,
+                               e->stream));
+            papr_launch_seqsum(ch.d, ch.m, e->d_tile_code + tile0, e->d_tile_run + 2 * tile0,
+                               (int)std::min<u64>((u64)e->num_sms, nt), e->stream);
+            e->launches += 1;
+            e->h2d += nt * 2;
+        }
+        release(ch.c);
+        return PAPR_OK;
+    };
+    rc = stream_chunks(e, src, g, resident, [&](const float *d, u64 off, u64 m, u64 c, bool last, const ChunkRelease &release) -> int {
+        int r = enqueue_scan(e, true, false, d, m, g.first + off, false);
+        if (r) return r;
+        if (!inline_exact) { release(c); return PAPR_OK; }
+        const u64 tile0 = off / PAPR_SEQ_TILE, nt = (m + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
+        papr_launch_tilesum(d, m, e->d_tile_sum + tile0, (int)std::min<u64>((u64)e->num_sms * 2, nt), e->stream);
+        e->launches += 1;
+        CU(cudaMemcpyAsync(e->h_tile_sum + tile0, e->d_tile_sum + tile0, nt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->seq_ev[c % kSeqEvents], e->stream));
+        e->d2h += nt * 8;
+        pend.push_back({d, off, m, c});
+        while (pend.size() - pend_head > (size_t)(last ? 0 : (resident ? kSeqLagResident : kSeqLagRing)))
+            if ((r = process(pend[pend_head++], release))) return r;
+        return PAPR_OK;
+    });
+    if (rc) return rc;
+    papr_launch_stats_finalize(e->d_work->wp, e->grid, g.n, &e->d_out->local, e->stream);
+    e->launches += 1;
+    CU(cudaGetLastError());
+    if (!seq_ok || ntiles == 0) return PAPR_OK;
+    // the runs come back, the host chains them in file order, the exact sum replaces the tree sum
+    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->d2h += ntiles * 16;
+    double s = 0.0;
+    if ((rc = seq_chain(e, g.n, &s, tile_fetcher(e, src, g, resident)))) return rc;
+    e->h_out->pre4[0] = s;
+    CU(cudaMemcpyAsync(&e->d_out->local.sum, &e->h_out->pre4[0], sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    *exact_done = true;
+    return PAPR_OK;
+}
+
+// CCDF pass of the re-streaming mode: the capture crosses PCIe a second time, chunk by chunk
+static int host_hist_streamed(papr_engine *e, const HostSource &src, const StreamGeom &g)
+{
+    int rc;
+    if ((rc = hist_begin(e))) return rc;
+    rc = stream_chunks(e, src, g, false, [&](const float *d, u64, u64 m, u64 c, bool, const ChunkRelease &release) -> int {
+        int r = hist_chunk(e, d, m, false);
+        release(c);
+        return r;
+    });
+    if (rc) return rc;
+    return hist_end(e);
+}
+
+// NaN sign (see fix_nan_sign) when the shard is not resident: one more pass, only ever taken for
+// captures larger than HBM that contain a NaN
+static int fix_nan_sign_streamed(papr_engine *e, const HostSource &src, const StreamGeom &g, papr_stats *st)
+{
+    if (!std::isnan(st->sum) || g.n == 0) return PAPR_OK;
+    CU(cudaMemsetAsync(e->d_nan_idx, 0xff, sizeof(u64), e->stream));
+    int rc = stream_chunks(e, src, g, false, [&](const float *d, u64 off, u64 m, u64 c, bool, const ChunkRelease &release) -> int {
+        papr_launch_find_nan(d, m, g.first + off, e->d_nan_idx, e->num_sms * 8, e->stream);
+        e->launches += 1;
+        release(c);
+        return PAPR_OK;
+    });
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&e->h_out->nan_idx, e->d_nan_idx, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const u64 k = e->h_out->nan_idx;
+    if (k == ~0ull) return PAPR_OK;
+    float pair[2];
+    if ((rc = tile_fetcher(e, src, g, false)(k - g.first, 1, pair))) return rc;
+    const bool neg = std::isnan(pair[1]) ? std::signbit(pair[1]) : std::signbit(pair[0]);
+    st->sum = std::copysign(std::fabs(st->sum), neg ? -1.0 : 1.0);
+    return PAPR_OK;
+}
+
+static bool is_pinned_host(const void *p, u64 bytes)
+{
+    cudaPointerAttributes attr;
+    const bool pinned = bytes && cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return pinned;
+}
+
+static HostSource memory_source(const void *image, u64 bytes)
+{
+    static const unsigned char none = 0;
+    HostSource src;
+    src.img = image ? (const unsigned char *)image : &none; // empty capture
+    src.bytes = bytes;
+    src.pinned = is_pinned_host(image, bytes);
+    return src;
+}
+
+static int analyze_source(papr_engine *e, const HostSource &src, int graph, papr_result *out)
+{
     graph = graph ? 1 : 0;
     begin_analysis(e);
     memset(out, 0, offsetof(papr_result, level));
     out->mode_used = PAPR_MODE_TWO_PASS;
     int rc;
-    u64 n = 0;
+    StreamGeom g;
+    if ((rc = make_geom(e, src, 0, nullptr, &g))) return rc;
+    const bool resident = fits_resident(e, g.n * 8 + 16);
+    e->streamed = !resident;
     const bool trace = getenv("PAPR_B200_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto mark = [&](const char *what) {
@@ -1033,27 +1363,72 @@ extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t byt
             fprintf(stderr, "papr_b200 trace: %-34s %9.3f ms\n", what,
                     std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     };
+    if (resident) rc = ensure_device_buffer(e, g.n * 8 + 16);
+    else rc = ensure_ring(e);
+    if (rc) return rc;
+    if (!src.pinned && g.npairs && (rc = ensure_staging(e))) return rc;
+    mark(resident ? "buffers (resident shard)" : "buffers (re-streaming ring)");
     CU(cudaEventRecord(e->ev_begin, e->stream));
-    if ((rc = host_stream_stats(e, image, bytes, 0, &n))) return rc;
-    mark("buffers + staging + H2D enqueued");
-    if (trace) { CU(cudaStreamSynchronize(e->stream)); mark("H2D + pass 1 complete"); }
-    if ((rc = enqueue_finalize_levels_exact(e, e->d_buf, n, graph, e->exact_sum != 0))) return rc;
-    mark("finalize (+ exact sum)");
-    if ((rc = enqueue_hist_exact(e, e->d_buf, n, true))) return rc;
+    bool exact_done = false;
+    if ((rc = host_pass1(e, src, g, resident, e->exact_sum != 0, &exact_done))) return rc;
+    mark("H2D + pass 1 (+ exact sum)");
+    // local state -> merged state, avg, L, levels on the device
+    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
+                       &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
+    e->launches += 1;
+    if (resident) rc = enqueue_hist_exact(e, e->d_buf, g.n, true);
+    else rc = host_hist_streamed(e, src, g);
+    if (rc) return rc;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     mark("CCDF pass + fetch");
     stats_to_host(e->h_out->o.merged, &out->stats);
-    if ((rc = fix_nan_sign(e, e->d_buf, n, 0, &out->stats))) return rc;
-    if (collect(e, graph, out, true)) {
-        rc = run_exact_ccdf(e, e->d_buf, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
+    if (resident) rc = fix_nan_sign(e, e->d_buf, g.n, 0, &out->stats);
+    else rc = fix_nan_sign_streamed(e, src, g, &out->stats);
+    if (rc) return rc;
+    if (collect(e, graph, out, true)) { // device level table != host libm's: redo with the host's
+        if (resident) {
+            rc = run_exact_ccdf(e, e->d_buf, g.n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
+        } else {
+            if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
+            if ((rc = enqueue_reset(e))) return rc;
+            if ((rc = host_hist_streamed(e, src, g))) return rc;
+            if ((rc = enqueue_fetch(e))) return rc;
+            CU(cudaStreamSynchronize(e->stream));
+            if (e->h_out->o.counts[PAPR_MAX_LEVELS] != 0) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+            for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)e->h_out->o.counts[j];
+        }
         if (rc) return rc;
         CU(cudaEventRecord(e->ev_end, e->stream));
         CU(cudaStreamSynchronize(e->stream));
     }
     finish_timing(e, out);
     return PAPR_OK;
+}
+
+extern "C" int papr_analyze_host(papr_engine *e, const void *image, uint64_t bytes, int graph, papr_result *out)
+{
+    if (!e || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    cudaSetDevice(e->device);
+    return analyze_source(e, memory_source(image, bytes), graph, out);
+}
+
+// pass 1 of a host-side shard that must stay resident (sharded callers run their own exchange
+// before the CCDF pass); nothing synchronised on return
+static int host_stream_stats(papr_engine *e, const HostSource &src, u64 first, u64 *n_out,
+                             const float *tail_override = nullptr)
+{
+    StreamGeom g;
+    int rc;
+    if ((rc = make_geom(e, src, first, tail_override, &g))) return rc;
+    *n_out = g.n;
+    if (!fits_resident(e, g.n * 8 + 16))
+        return fail(e, PAPR_ERR_ARG, "shard exceeds the resident budget of this GPU: use more shards");
+    if ((rc = ensure_device_buffer(e, g.n * 8 + 16))) return rc;
+    if (!src.pinned && g.npairs && (rc = ensure_staging(e))) return rc;
+    bool exact_done = false;
+    return host_pass1(e, src, g, true, false, &exact_done);
 }
 
 // Sharded callers with host-resident shards: pass 1 while streaming in; the shard stays resident at
@@ -1065,9 +1440,8 @@ extern "C" int papr_stats_host(papr_engine *e, const void *image, uint64_t bytes
     begin_analysis(e);
     int rc;
     u64 n = 0;
-    if ((rc = host_stream_stats(e, image, bytes, first, &n))) return rc;
-    papr_launch_stats_finalize(e->d_work->wp, e->grid, n, &e->d_out->local, e->stream);
-    e->launches += 1;
+    cudaSetDevice(e->device);
+    if ((rc = host_stream_stats(e, memory_source(image, bytes), first, &n))) return rc;
     CU(cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     stats_to_host(e->h_out->o.local, out);
@@ -1076,12 +1450,12 @@ extern "C" int papr_stats_host(papr_engine *e, const void *image, uint64_t bytes
     return fix_nan_sign(e, e->d_buf, n, first, out);
 }
 
-// The capture as one host image: mmap for regular files; anything else (FIFO, character device - the
-// reference needs a seekable file, papr.c:142, we do not) is read to the end into memory.
-struct FileImage {
-    void *ptr = nullptr;
-    size_t bytes = 0;
-    bool mapped = false;
+// The capture behind a path: a regular file is read with pread() chunk by chunk (page cache ->
+// pinned staging, no mapping); anything else (FIFO, character device - the reference needs a seekable
+// file, papr.c:142, we do not) is read to the end into memory first.
+struct FileSource {
+    HostSource src;
+    void *owned = nullptr;
     int open(const char *path, std::string &err)
     {
         int fd = ::open(path, O_RDONLY);
@@ -1089,43 +1463,43 @@ struct FileImage {
         struct stat sb;
         if (fstat(fd, &sb) != 0) { ::close(fd); err = "fstat failed"; return PAPR_ERR_IO; }
         if (S_ISREG(sb.st_mode)) {
-            bytes = (size_t)sb.st_size;
-            if (bytes) {
-                ptr = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
-                if (ptr == MAP_FAILED) { ptr = nullptr; ::close(fd); err = "mmap failed"; return PAPR_ERR_IO; }
-                madvise(ptr, bytes, MADV_WILLNEED);
-                mapped = true;
-            }
-        } else {
-            size_t cap = 1u << 24;
-            char *buf = (char *)malloc(cap);
-            for (;;) {
-                if (!buf) { ::close(fd); err = "out of memory reading the stream"; return PAPR_ERR_IO; }
-                ssize_t got = ::read(fd, buf + bytes, cap - bytes);
-                if (got < 0) { free(buf); ::close(fd); err = "read failed"; return PAPR_ERR_IO; }
-                if (got == 0) break;
-                bytes += (size_t)got;
-                if (bytes == cap) buf = (char *)realloc(buf, cap *= 2);
-            }
-            ptr = buf;
+            src.fd = fd;
+            src.bytes = (u64)sb.st_size;
+            posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+            return PAPR_OK;
+        }
+        size_t cap = 1u << 24, bytes = 0;
+        char *buf = (char *)malloc(cap);
+        for (;;) {
+            if (!buf) { ::close(fd); err = "out of memory reading the stream"; return PAPR_ERR_IO; }
+            ssize_t got = ::read(fd, buf + bytes, cap - bytes);
+            if (got < 0 && errno == EINTR) continue;
+            if (got < 0) { free(buf); ::close(fd); err = "read failed"; return PAPR_ERR_IO; }
+            if (got == 0) break;
+            bytes += (size_t)got;
+            if (bytes == cap) buf = (char *)realloc(buf, cap *= 2);
         }
         ::close(fd);
+        owned = buf;
+        src.img = (const unsigned char *)buf;
+        src.bytes = bytes;
         return PAPR_OK;
     }
-    ~FileImage()
+    ~FileSource()
     {
-        if (ptr && mapped) munmap(ptr, bytes);
-        else free(ptr);
+        if (src.fd >= 0) ::close(src.fd);
+        free(owned);
     }
 };
 
 extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)
 {
     if (!e || !path || !out) return PAPR_ERR_ARG;
-    FileImage f;
+    cudaSetDevice(e->device);
+    FileSource f;
     int rc = f.open(path, e->err);
     if (rc) return rc;
-    return papr_analyze_host(e, f.ptr, f.bytes, graph, out);
+    return analyze_source(e, f.src, graph, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1259,18 +1633,16 @@ extern "C" int papr_multi_set(papr_multi *m, const char *name, double value)
     return PAPR_OK;
 }
 
-extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_t bytes, int graph, papr_result *out)
+static int multi_analyze_source(papr_multi *m, const HostSource &whole, int graph, papr_result *out)
 {
-    if (!m || !out || (bytes && !image)) return PAPR_ERR_ARG;
     graph = graph ? 1 : 0;
     const int N = m->n;
-    const unsigned char *img = (const unsigned char *)image;
-    const u64 nfloats = bytes / 4, npairs = nfloats / 2;
+    const u64 bytes = whole.bytes, nfloats = bytes / 4, npairs = nfloats / 2;
     const bool tail = (nfloats & 1) != 0;
     float tail_pair[2] = {0.f, 0.f};
     if (tail) {
-        memcpy(&tail_pair[0], img + 4 * (nfloats - 1), 4);
-        tail_pair[1] = papr_host_stale_q(img, bytes); // needs the WHOLE image: the stale Q may sit in another shard
+        if (!whole.read(&tail_pair[0], 4 * (nfloats - 1), 4)) { m->err = "read failed"; return PAPR_ERR_IO; }
+        tail_pair[1] = stale_q_of(whole); // needs the WHOLE capture: the stale Q may sit in another shard
     }
     // shard = whole chunks (so chunk, batch and tile boundaries coincide with shard boundaries)
     const u64 chunk_samples = m->eng[0]->chunk_bytes / 8;
@@ -1302,9 +1674,9 @@ extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_
         auto step = [&](int rc) { if (rc < 0 && !failed.exchange(true)) { rcs[r] = rc; } return rc; };
         begin_analysis(e);
         // pass 1 while the shard streams in
-        if (!failed) step(host_stream_stats(e, img + lo * 8, (hi - lo) * 8, lo, &ns[r], (tail && r == tail_rank) ? tail_pair : nullptr));
+        cudaSetDevice(e->device);
+        if (!failed) step(host_stream_stats(e, whole.slice(lo * 8, (hi - lo) * 8), lo, &ns[r], (tail && r == tail_rank) ? tail_pair : nullptr));
         if (!failed) {
-            papr_launch_stats_finalize(e->d_work->wp, e->grid, ns[r], &e->d_out->local, e->stream);
             cudaMemcpyAsync(&e->h_out->o.local, &e->d_out->local, sizeof(PaprDevStats), cudaMemcpyDeviceToHost, e->stream);
             if (cudaStreamSynchronize(e->stream) != cudaSuccess) step(fail(e, PAPR_ERR_CUDA, cudaGetErrorString(cudaGetLastError())));
             stats_to_host(e->h_out->o.local, &st[r]);
@@ -1334,7 +1706,7 @@ extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_
             if (exact_ok) {
                 double s = 0.0;
                 for (int q = 0; q < N; ++q)
-                    if (seq_chain(m->eng[q], m->eng[q]->d_buf, ns[q], &s) < 0) { failed = true; rcs[0] = PAPR_ERR_CUDA; }
+                    if (seq_chain_resident(m->eng[q], m->eng[q]->d_buf, ns[q], &s) < 0) { failed = true; rcs[0] = PAPR_ERR_CUDA; }
                 merged.sum = s;
             }
             out->stats = merged;
@@ -1395,11 +1767,18 @@ extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_
     return PAPR_OK;
 }
 
+extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_t bytes, int graph, papr_result *out)
+{
+    if (!m || !out || (bytes && !image)) return PAPR_ERR_ARG;
+    cudaSetDevice(m->eng[0]->device);
+    return multi_analyze_source(m, memory_source(image, bytes), graph, out);
+}
+
 extern "C" int papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out)
 {
     if (!m || !path || !out) return PAPR_ERR_ARG;
-    FileImage f;
+    FileSource f;
     int rc = f.open(path, m->err);
     if (rc) return rc;
-    return papr_multi_analyze_host(m, f.ptr, f.bytes, graph, out);
+    return multi_analyze_source(m, f.src, graph, out);
 }

@@ -106,6 +106,7 @@ int papr_main(int argc, char **argv)
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
         if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
+        if ((v = getenv("PAPR_B200_MAX_RESIDENT_MB"))) papr_engine_set(e, "max_resident_bytes", atof(v) * 1048576.0);
         const double t1 = now_ms();
         int rc = papr_analyze_file(e, path, graph, r);
         const double t2 = now_ms();

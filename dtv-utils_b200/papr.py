@@ -61,7 +61,7 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_engine_device_buffer", "papr_shard_presample_async", "papr_shard_scan_async",
                "papr_shard_counts_async", "papr_shard_finish", "papr_multi_create", "papr_multi_destroy",
                "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
-               "papr_multi_exchange"]
+               "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -117,6 +117,9 @@ def load_library(path: Optional[str] = None):
     lib.papr_multi_last_error.restype = C.c_char_p
     lib.papr_multi_exchange.argtypes = [vp]
     lib.papr_multi_exchange.restype = C.c_char_p
+    lib.papr_seqsum_prepare.argtypes = [vp, vp, u64, C.POINTER(C.c_double)]
+    lib.papr_seqsum_runs.argtypes = [vp, vp, u64, C.c_double]
+    lib.papr_seqsum_chain.argtypes = [vp, vp, u64, C.POINTER(C.c_double)]
     if path is None:
         _lib = lib
     return lib
@@ -281,6 +284,22 @@ class Engine:
                          "papr_fused_counts")
         return rc == 1, cnt
 
+    # exact sequential sum across shards (papr.c:104; see include/papr_b200.h) ---------------------
+    def seqsum_prepare(self, d_iq, nsamples: int) -> float:
+        a = C.c_double()
+        self._check(self.lib.papr_seqsum_prepare(self.h, _ptr(d_iq), nsamples, C.byref(a)), "papr_seqsum_prepare")
+        return a.value
+
+    def seqsum_runs(self, d_iq, nsamples: int, pre: float) -> bool:
+        """-> applicable (False: a tile sum is NaN/Inf, so is the reference's sum)"""
+        return self._check(self.lib.papr_seqsum_runs(self.h, _ptr(d_iq), nsamples, float(pre)),
+                           "papr_seqsum_runs") == 0
+
+    def seqsum_chain(self, d_iq, nsamples: int, state: float) -> float:
+        s = C.c_double(state)
+        self._check(self.lib.papr_seqsum_chain(self.h, _ptr(d_iq), nsamples, C.byref(s)), "papr_seqsum_chain")
+        return s.value
+
     # stream-ordered stages (see include/papr_b200.h) ---------------------------------------------------
     def device_buffer(self, which: int, dtype):
         """torch tensor aliasing one of the engine's exchange buffers (zero copy)."""
@@ -376,18 +395,26 @@ class MultiEngine:
 
 # ---- byte-range sharding over ranks (one process per GPU, torch.distributed) -----------------------
 def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, mode: int = MODE_TWO_PASS,
-                    group=None, host_image=None) -> PaprResult:
+                    group=None, host_image=None, exact_sum: Optional[bool] = None) -> PaprResult:
     """Each rank holds samples [first_index, first_index+nsamples) of one capture; ranks are in index
     order.  Two tiny exchanges, no data-path collective: all-gather of the pass-1 states (merged in
     rank order on every rank, so first occurrences and the level table are identical everywhere) and
     one all-reduce (sum) of the integer level counts.  Returns the whole-capture result on every rank.
+
+    exact_sum: emulate the reference's sequential double sum (papr.c:104) bit for bit across the
+    ranks (tile runs computed in parallel, chained rank after rank; adds world_size tiny broadcasts).
+    Default (None): on for host-resident shards, like the engine's own file/host path; off for
+    device-resident shards, whose merged fixed-order tree sums agree with it to ~1e-15 relative.
     """
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     backend = dist.get_backend(group) if dist.is_initialized() else "none"
-    if backend == "nccl" and isinstance(engine, Engine) and host_image is None:
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if exact_sum is None:
+        exact_sum = host_image is not None
+    if backend == "nccl" and isinstance(engine, Engine) and host_image is None and not exact_sum:
         return _analyze_sharded_stream_ordered(engine, d_iq, nsamples, first_index, bool(graph), mode, group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     graph = bool(graph)
@@ -425,6 +452,8 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
     else:
         local = engine.stats_shard(d_iq, nsamples, first_index)
     merged = merge_stats(gather_stats(local))
+    if exact_sum and merged.sum == merged.sum and abs(merged.sum) != float("inf"):
+        merged.sum = _chain_sequential_sum(engine, d_iq, nsamples, rank, world, dev, group, merged.sum)
     _avg, _papr, lv = levels(merged, graph)
     L = len(lv)
     counts = [0] * L
@@ -436,6 +465,43 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
         if miss:  # two-pass mode, or some rank's thresholds fell outside its predicted windows
             counts, _ = allreduce_counts(engine.ccdf_shard(d_iq, nsamples, lv))
     return result_from_parts(merged, graph, counts)
+
+
+def _chain_sequential_sum(engine, d_iq, nsamples, rank, world, dev, group, fallback):
+    """papr.c:104 across ranks: every rank reduces its tiles to parity-transducer runs in parallel
+    (papr_seqsum_prepare / _runs); the running sum is then handed from rank to rank in index order
+    (papr_seqsum_chain), one 8-byte broadcast per rank.  Returns `fallback` when some rank reports
+    that the emulation does not apply."""
+    import torch
+    import torch.distributed as dist
+
+    approx = engine.seqsum_prepare(d_iq, nsamples)
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = approx
+        dist.all_reduce(t, group=group)     # one non-zero contribution per slot: an all-gather
+        parts = t.tolist()
+    else:
+        parts = [approx]
+    pre = 0.0
+    for q in range(rank):
+        pre += parts[q]
+    ok = engine.seqsum_runs(d_iq, nsamples, pre)
+    if world > 1:
+        f = torch.tensor([0 if ok else 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(f, group=group)
+        ok = int(f.item()) == 0
+    if not ok:
+        return fallback
+    state = 0.0
+    for r in range(world):                  # the only sequential part: ~1 ms of host work per rank
+        if rank == r:
+            state = engine.seqsum_chain(d_iq, nsamples, state)
+        if world > 1:
+            t = torch.tensor([state], dtype=torch.float64, device=dev)
+            dist.broadcast(t, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+            state = float(t.item())
+    return state
 
 
 def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group):

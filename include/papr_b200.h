@@ -91,7 +91,9 @@ const char *papr_last_error(const papr_engine *e); /* e may be NULL: last create
 /* cudaStream_t the engine launches on (for callers that time or order against it). */
 void *papr_engine_stream(papr_engine *e);
 /* Tunables by name ("mode", "presample_stride", "window_sigmas", "chunk_bytes", "staging_threads",
- * "fused_min_samples", "fine_bytes_log2", "exact_sum": -1 (default) = emulate the reference's sequential
+ * "fused_min_samples", "fine_bytes_log2", "max_resident_bytes": host-side captures larger than this
+ * (default 0 = what the GPU has free, less 1 GiB) are not kept resident in HBM but streamed twice,
+ * like the reference reads its file twice (papr.c:142); "exact_sum": -1 (default) = emulate the reference's sequential
  * double sum (papr.c:104) bit for bit on the file/host path only, 0 = never, 1 = also on the
  * device-resident path).  Returns PAPR_ERR_ARG for an unknown name. */
 int  papr_engine_set(papr_engine *e, const char *name, double value);
@@ -106,13 +108,16 @@ int papr_main(int argc, char **argv);
 /* ---- whole analysis: replaces papr.c:100-190 minus the printf calls --------------------------- */
 /* Host buffer holding the FILE IMAGE (any length; a trailing lone I is paired with the stale Q
  * exactly as the reference's chunked fread does, papr.c:100-103).  Pinned or pageable; streamed to
- * the GPU through double-buffered cudaMemcpyAsync with the statistics pass overlapped. */
+ * the GPU in chunks (cudaMemcpyAsync straight from pinned memory, through a pinned staging ring
+ * otherwise) with the statistics pass and the sequential-sum emulation running on each chunk as it
+ * lands, so that only the CCDF pass over the now-resident shard remains after the last byte. */
 int papr_analyze_host(papr_engine *e, const void *file_image, uint64_t file_bytes, int graph,
                       papr_result *out);
 /* Device-resident complete samples. */
 int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t nsamples, int graph,
                         papr_result *out);
-/* Open + mmap + papr_analyze_host. */
+/* The same for a file: regular files are read with pread() straight into the pinned staging ring
+ * (no mapping); FIFOs and other streams are read to the end first (no seek needed, unlike papr.c:142). */
 int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out);
 
 /* ---- one capture over several GPUs of this box (single process) --------------------------------- */
@@ -174,6 +179,20 @@ int papr_shard_scan_async(papr_engine *e, const float *d_iq, uint64_t nsamples, 
 int papr_shard_counts_async(papr_engine *e, const void *d_all_stats, int nparts, int graph, int fused,
                             const float *d_iq, uint64_t nsamples);
 int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
+
+/* papr.c:104 for a capture sharded over ranks: the reference's SEQUENTIAL double sum, bit for bit
+ * (DESIGN.md section 5).  On the resident shard [d_iq, d_iq + 2*nsamples) of every rank:
+ *   prepare -> *approx = sum of this shard (any order); the caller all-gathers these and forms
+ *              pre = the sum of approx over the LOWER ranks;
+ *   runs    -> places the shard's 32768-sample tiles in binades of the running sum (from pre) and
+ *              reduces each tile to its parity-transducer run on the GPU; returns 1 if not applicable
+ *              (a non-finite tile sum: the reference's sum is NaN/Inf as well);
+ *   chain   -> rank after rank in index order: *state is the exact running sum after all lower
+ *              ranks (0.0 on rank 0) on entry and after this shard on return; the caller hands it on.
+ * The last rank's state replaces papr_stats.sum of the merged statistics. */
+int papr_seqsum_prepare(papr_engine *e, const float *d_iq, uint64_t nsamples, double *approx);
+int papr_seqsum_runs(papr_engine *e, const float *d_iq, uint64_t nsamples, double pre);
+int papr_seqsum_chain(papr_engine *e, const float *d_iq, uint64_t nsamples, double *state);
 
 /* papr.c:132-135,154-161 / 186-190: the exact stdout text.  Returns its length, or <0. */
 long papr_format(const papr_result *r, char *out, size_t cap);

@@ -65,7 +65,7 @@ def test_host_buffer_path_equals_reference(built, eng, name, graph, manifest):
     for chunk in (64 << 20, 1 << 20):  # one chunk / many chunks (+ the staging ring wrapping around)
         eng.set("chunk_bytes", chunk)
         assert built.format_result(eng.analyze_host(img, graph=graph)) == _gold(name, graph)
-    eng.set("chunk_bytes", 64 << 20)
+    eng.set("chunk_bytes", 16 << 20)
 
 
 @pytest.mark.parametrize("mode", [1, 2], ids=["two_pass", "fused"])
@@ -84,6 +84,27 @@ def test_device_path_equals_reference(built, eng, torch_cuda, name, graph, mode,
         eng.set("mode", 0)
     assert built.format_result(res) == _gold(name, graph)
     assert res.mode_used == mode
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+@pytest.mark.parametrize("name", list(fixtures.FIXTURES))
+def test_capture_larger_than_hbm_is_restreamed(built, eng, name, graph, manifest, tmp_path):
+    """A capture that does not fit the resident budget (forced here: 1 MiB) is streamed twice through a
+    ring of device chunk buffers - the reference reads its file twice as well (papr.c:142).  Host image
+    and file (pread) sources, all fixtures incl. NaN sign, lone-I tails and the empty file."""
+    img = fixtures.image(name)
+    if fixtures.md5(img) != manifest[name]["input_md5"]:
+        pytest.skip("fixture drift (different numpy RNG stream)")
+    path = tmp_path / "capture.cfile"
+    path.write_bytes(img)
+    eng.set("chunk_bytes", 1 << 20)
+    eng.set("max_resident_bytes", 1 << 20)
+    try:
+        assert built.format_result(eng.analyze_host(img, graph=graph)) == _gold(name, graph)
+        assert built.format_result(eng.analyze_file(str(path), graph)) == _gold(name, graph)
+    finally:
+        eng.set("max_resident_bytes", 0)
+        eng.set("chunk_bytes", 16 << 20)
 
 
 def test_pinned_source_goes_direct(built, eng, torch_cuda):
@@ -283,9 +304,54 @@ def test_exact_sequential_sum_bit_for_bit(built, eng, torch_cuda):
                 res = eng.analyze_host(f, graph=graph)
                 assert struct.pack("<d", res.stats.sum) == struct.pack("<d", st.sum), name
                 assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), graph), name
+            # many chunks: tile sums / binade placement / tile runs trail the copies chunk by chunk;
+            # resident shard, then the re-streaming mode (ring of device chunk buffers, two PCIe passes)
+            eng.set("chunk_bytes", 1 << 20)
+            try:
+                for budget in (0, 1 << 20):
+                    eng.set("max_resident_bytes", budget)
+                    res = eng.analyze_host(f, graph=False)
+                    assert struct.pack("<d", res.stats.sum) == struct.pack("<d", st.sum), (name, budget)
+                    assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), False), (name, budget)
+            finally:
+                eng.set("max_resident_bytes", 0)
+                eng.set("chunk_bytes", 16 << 20)
     finally:
         eng.set("exact_sum", -1)
         eng.set("mode", 0)
+
+
+def test_exact_sequential_sum_chained_over_shards(built, torch_cuda):
+    """papr_seqsum_prepare/_runs/_chain: three shards (one engine each, as three ranks would hold them),
+    tile runs per shard, the running sum handed on in index order == the reference's sequential sum
+    over the whole capture, bit for bit - for cuts that are NOT tile aligned."""
+    import struct
+    engines = [built.Engine(0) for _ in range(3)]
+    try:
+        for name, f in _seq_cases():
+            f = np.ascontiguousarray(f, np.float32)
+            n = f.size // 2
+            st, *_ = oracle_binding.analyze(f, False)
+            cuts = [0, (n // 3 + 1001) & ~1, (2 * n // 3 + 7) & ~1, n]
+            shards = [_dev(torch_cuda, f[2 * cuts[r]:2 * cuts[r + 1]]) for r in range(3)]
+            ns = [cuts[r + 1] - cuts[r] for r in range(3)]
+            approx = [engines[r].seqsum_prepare(shards[r], ns[r]) for r in range(3)]
+            assert abs(sum(approx) - st.sum) <= 1e-9 * abs(st.sum)
+            for r in range(3):
+                assert engines[r].seqsum_runs(shards[r], ns[r], sum(approx[:r])), name
+            state = 0.0
+            for r in range(3):
+                state = engines[r].seqsum_chain(shards[r], ns[r], state)
+            assert struct.pack("<d", state) == struct.pack("<d", st.sum), name
+        # a non-finite sample: the emulation reports "not applicable" instead of inventing a sum
+        bad = fixtures.siggen(0, 100_000, 5).copy()
+        bad[12345] = np.inf
+        d = _dev(torch_cuda, bad)
+        engines[0].seqsum_prepare(d, 100_000)
+        assert engines[0].seqsum_runs(d, 100_000, 0.0) is False
+    finally:
+        for e in engines:
+            e.close()
 
 
 def test_ofdm_producer_capture_against_oracle(built, eng, torch_cuda):

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, graph, fused, q):
+def _worker(rank, world, port, name, graph, fused, exact, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -54,6 +54,21 @@ def _worker(rank, world, port, name, graph, fused, q):
         def fused_counts(self, merged, graph):
             return rank == 1, [0] * 2048
 
+        # exact sequential sum stages: literal float64 adds in file order (np.cumsum is sequential)
+        def _powers(self, iq, n):
+            i, q = iq[0:2 * n:2], iq[1:2 * n:2]
+            return (i * i + q * q).astype(np.float32).astype(np.float64)  # three float32 roundings, papr.c:103
+
+        def seqsum_prepare(self, iq, n):
+            return float(np.sum(self._powers(iq, n)))
+
+        def seqsum_runs(self, iq, n, pre):
+            self.pre_seen = pre
+            return True
+
+        def seqsum_chain(self, iq, n, state):
+            return float(np.cumsum(np.concatenate([[state], self._powers(iq, n)]))[-1])
+
     f = np.frombuffer(fixtures.image(name), np.float32)
     ntot = f.size // 2
     cut = (ntot // 2) & ~1
@@ -62,19 +77,26 @@ def _worker(rank, world, port, name, graph, fused, q):
     eng.total = ntot
     shard = np.ascontiguousarray(f[2 * lo:2 * hi])
     res = pb.analyze_sharded(eng, shard, hi - lo, lo, graph,
-                             mode=pb.papr.MODE_FUSED if fused else pb.papr.MODE_TWO_PASS)
+                             mode=pb.papr.MODE_FUSED if fused else pb.papr.MODE_TWO_PASS, exact_sum=exact)
+    if exact:  # the running sum was handed from rank 0 to rank 1: equal to the whole-file sequential sum
+        import struct
+        whole, *_ = oracle_binding.analyze(f, False)
+        assert struct.pack("<d", res.stats.sum) == struct.pack("<d", whole.sum)
+        if rank == 1:
+            assert abs(eng.pre_seen - float(np.sum(eng._powers(f, cut)))) < 1e-9 * max(1e-300, abs(eng.pre_seen))
     q.put((rank, pb.format_result(res)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,graph,fused", [("ties", False, False), ("appA_300k_s7", True, False),
-                                               ("burst", False, True), ("neg_only", True, True)])
-def test_two_rank_sharding_matches_reference(name, graph, fused, built):
+@pytest.mark.parametrize("name,graph,fused,exact", [("ties", False, False, False), ("appA_300k_s7", True, False, True),
+                                                     ("burst", False, True, False), ("neg_only", True, True, True),
+                                                     ("gauss_1M", False, False, True)])
+def test_two_rank_sharding_matches_reference(name, graph, fused, exact, built):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() + hash((name, graph)) % 97) % 400
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, graph, fused, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, graph, fused, exact, q)) for r in range(2)]
     for p in procs:
         p.start()
     outs = dict(q.get(timeout=120) for _ in procs)
