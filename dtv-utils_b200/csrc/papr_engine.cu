@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -35,7 +36,7 @@ typedef unsigned long long u64;
 
 namespace {
 
-constexpr int kStages = 4;                 // pinned staging buffers for pageable / file sources
+constexpr int kMaxStages = 34;             // pinned staging slots for pageable / file sources (threads + 2)
 constexpr int kRing = 4;                   // device chunk buffers of the re-streaming (capture > HBM) mode
 constexpr int kSeqLagRing = 3;             // chunks between a chunk's tile sums and its tile runs (< kRing) ...
 constexpr int kSeqLagResident = 6;         // ... and when nothing limits how far the copies run ahead (< kSeqEvents)
@@ -73,69 +74,6 @@ struct HostOut {
 
 std::string g_create_error;
 
-// fork-join helper threads that fill a pinned staging buffer from a pageable image (memcpy) or a
-// file (pread), each worker one page-aligned slice of the chunk
-class CopyPool {
-public:
-    typedef std::function<bool(size_t lo, size_t hi)> SliceFn;
-    explicit CopyPool(int n) : stop_(false), pending_(0), gen_(0)
-    {
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
-    }
-    ~CopyPool()
-    {
-        {
-            std::lock_guard<std::mutex> l(m_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto &t : workers_) t.join();
-    }
-    // fn(lo, hi) for disjoint slices covering [0, bytes); false if any slice failed
-    bool parallel(size_t bytes, const SliceFn &fn)
-    {
-        if (workers_.empty() || bytes < (1u << 20)) return fn(0, bytes);
-        {
-            std::lock_guard<std::mutex> l(m_);
-            fn_ = &fn; bytes_ = bytes; ok_ = true;
-            pending_ = (int)workers_.size();
-            ++gen_;
-        }
-        cv_.notify_all();
-        std::unique_lock<std::mutex> l(m_);
-        done_.wait(l, [this] { return pending_ == 0; });
-        return ok_;
-    }
-
-private:
-    void run(int id)
-    {
-        u64 seen = 0;
-        for (;;) {
-            std::unique_lock<std::mutex> l(m_);
-            cv_.wait(l, [&] { return stop_ || gen_ != seen; });
-            if (stop_) return;
-            seen = gen_;
-            size_t n = workers_.size(), per = (bytes_ / n + 4095) & ~(size_t)4095;
-            size_t lo = std::min(bytes_, per * id), hi = std::min(bytes_, lo + per);
-            const SliceFn *fn = fn_;
-            l.unlock();
-            bool ok = hi > lo ? (*fn)(lo, hi) : true;
-            l.lock();
-            if (!ok) ok_ = false;
-            if (--pending_ == 0) done_.notify_all();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex m_;
-    std::condition_variable cv_, done_;
-    bool stop_, ok_ = true;
-    int pending_;
-    u64 gen_;
-    const SliceFn *fn_ = nullptr;
-    size_t bytes_ = 0;
-};
-
 // where the capture's bytes come from: a memory image (pinned or pageable) or a regular file, read
 // with pread() straight into the pinned staging buffers (no page faults, no mapping to tear down)
 struct HostSource {
@@ -166,6 +104,87 @@ struct HostSource {
     }
 };
 
+// Fills the pinned staging slots of a pageable / file source ahead of the H2D copies: every helper
+// thread takes the next whole chunk, waits until the slot's previous tenant has crossed PCIe, and
+// reads the chunk into it (memcpy or pread); the main thread consumes the chunks in order.  No
+// per-chunk fork/join: the helpers run free, the slots bound how far they get ahead.
+class ChunkFeeder {
+public:
+    ChunkFeeder(int device, const HostSource &src, u64 nchunks, u64 chunk_bytes, u64 total_bytes, int threads,
+                void *const *slots, const cudaEvent_t *slot_done, int nslots)
+        : device_(device), src_(src), nchunks_(nchunks), chunk_bytes_(chunk_bytes), total_(total_bytes), slots_(slots),
+          slot_done_(slot_done), nslots_(nslots), state_(nchunks, 0)
+    {
+        const int n = (int)std::min<u64>((u64)std::max(1, threads), std::max<u64>(nchunks, 1));
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~ChunkFeeder()
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            abort_ = true;
+        }
+        cv_slot_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    // blocks until chunk c sits in its slot; nullptr if reading it failed
+    const void *wait_filled(u64 c)
+    {
+        std::unique_lock<std::mutex> l(m_);
+        cv_fill_.wait(l, [&] { return state_[c] != 0; });
+        return state_[c] == 1 ? slots_[c % nslots_] : nullptr;
+    }
+    // the H2D copy of chunk c has been enqueued and slot_done[c % nslots] recorded behind it
+    void issued(u64 c)
+    {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            issued_ = c + 1;
+        }
+        cv_slot_.notify_all();
+    }
+
+private:
+    void run()
+    {
+        cudaSetDevice(device_);
+        for (;;) {
+            u64 c;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                if (abort_ || next_ >= nchunks_) return;
+                c = next_++;
+                if (c >= (u64)nslots_) { // slot still holds chunk c - nslots until that one has been issued ...
+                    cv_slot_.wait(l, [&] { return abort_ || issued_ > c - nslots_; });
+                    if (abort_) return;
+                }
+            }
+            // ... and that copy (or, for the first chunks, whatever an earlier pass left in the slot) has
+            // crossed PCIe; a never-recorded event returns at once
+            cudaEventSynchronize(slot_done_[c % nslots_]);
+            const u64 off = c * chunk_bytes_, len = std::min(chunk_bytes_, total_ - off);
+            const bool ok = src_.read(slots_[c % nslots_], off, len);
+            {
+                std::lock_guard<std::mutex> l(m_);
+                state_[c] = ok ? 1 : 2;
+            }
+            cv_fill_.notify_all();
+        }
+    }
+    int device_;
+    const HostSource &src_;
+    u64 nchunks_, chunk_bytes_, total_;
+    void *const *slots_;
+    const cudaEvent_t *slot_done_;
+    int nslots_;
+    std::vector<char> state_; // 0 = not yet, 1 = filled, 2 = read error
+    u64 next_ = 0, issued_ = 0;
+    bool abort_ = false;
+    std::mutex m_;
+    std::condition_variable cv_fill_, cv_slot_;
+    std::vector<std::thread> workers_;
+};
+
 } // namespace
 
 struct papr_engine {
@@ -177,7 +196,7 @@ struct papr_engine {
     int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
     size_t chunk_bytes = 16u << 20; // measured on the file path: 16 MiB chunks stay in the host LLC
-    int staging_threads = -1;       // -1: min(16, hardware threads)
+    int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16]
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
@@ -202,11 +221,11 @@ struct papr_engine {
     // host path
     float *d_buf = nullptr;
     size_t d_buf_bytes = 0;
-    void *h_stage[kStages] = {};
+    void *h_stage[kMaxStages] = {};
     size_t h_stage_bytes = 0;
-    cudaEvent_t stage_done[kStages] = {};
+    int h_stage_slots = 0;
+    cudaEvent_t stage_done[kMaxStages] = {};
     cudaEvent_t chunk_ready = nullptr;
-    CopyPool *pool = nullptr;
     // re-streaming mode (capture larger than the resident budget): ring of device chunk buffers
     float *d_ring = nullptr;
     size_t d_ring_chunk = 0;
@@ -318,7 +337,6 @@ extern "C" int papr_engine_create(int device, papr_engine **out)
 extern "C" void papr_engine_destroy(papr_engine *e)
 {
     if (!e) return;
-    delete e->pool;
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_work); cudaFree(e->d_out); cudaFree(e->d_nan_idx); cudaFree(e->d_fine_base); cudaFree(e->d_fine);
     cudaFree(e->d_pre_cta); cudaFree(e->d_tile_sum); cudaFree(e->d_tile_code); cudaFree(e->d_tile_run);
@@ -350,7 +368,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "presample_stride") e->presample_stride = std::max(1, (int)v);
     else if (n == "window_sigmas") e->window_sigmas = (float)v;
     else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(kTileBytes - 1));
-    else if (n == "staging_threads") { e->staging_threads = std::max(-1, (int)v); delete e->pool; e->pool = nullptr; }
+    else if (n == "staging_threads") e->staging_threads = std::max(-1, (int)v);
     else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
     else if (n == "exact_sum") e->exact_sum = (int)v;
@@ -1088,17 +1106,23 @@ static int ensure_ring(papr_engine *e)
     return PAPR_OK;
 }
 
+static int staging_threads_of(const papr_engine *e)
+{
+    int n = e->staging_threads;
+    if (n < 0) n = std::min(16, std::max(2, (int)std::thread::hardware_concurrency() - 2));
+    return std::min(kMaxStages - 2, std::max(1, n));
+}
+
+// one pinned slot per helper thread plus two, so that a copy can be in flight while every helper reads
 static int ensure_staging(papr_engine *e)
 {
-    if (e->h_stage_bytes != e->chunk_bytes) {
+    const int slots = staging_threads_of(e) + 2;
+    if (e->h_stage_bytes != e->chunk_bytes || e->h_stage_slots != slots) {
         for (auto &p : e->h_stage) { if (p) cudaFreeHost(p); p = nullptr; }
-        for (auto &p : e->h_stage) CU(cudaHostAlloc(&p, e->chunk_bytes, cudaHostAllocDefault));
+        e->h_stage_bytes = 0;
+        for (int i = 0; i < slots; ++i) CU(cudaHostAlloc(&e->h_stage[i], e->chunk_bytes, cudaHostAllocDefault));
         e->h_stage_bytes = e->chunk_bytes;
-    }
-    if (!e->pool) {
-        int n = e->staging_threads;
-        if (n < 0) n = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
-        e->pool = new CopyPool(n);
+        e->h_stage_slots = slots;
     }
     return PAPR_OK;
 }
@@ -1164,10 +1188,14 @@ typedef std::function<int(const float *d_chunk, u64 off, u64 m, u64 c, bool last
 
 static int stream_chunks(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, const ChunkWork &work)
 {
-    int stage = 0, rc;
+    int rc;
     const ChunkRelease release = [&](u64 c) {
         if (!resident) cudaEventRecord(e->ring_free[c % kRing], e->stream);
     };
+    std::unique_ptr<ChunkFeeder> feeder; // helper threads stop and join when this goes out of scope
+    if (!src.pinned && g.npairs)
+        feeder.reset(new ChunkFeeder(e->device, src, (g.npairs + g.chunk_samples - 1) / g.chunk_samples, e->chunk_bytes,
+                                     g.npairs * 8, staging_threads_of(e), e->h_stage, e->stage_done, e->h_stage_slots));
     u64 c = 0;
     for (u64 off = 0; off < g.n; off += g.chunk_samples, ++c) {
         const u64 m = std::min(g.chunk_samples, g.n - off);               // samples of this chunk (incl. the tail sample)
@@ -1175,21 +1203,12 @@ static int stream_chunks(papr_engine *e, const HostSource &src, const StreamGeom
         float *dst = resident ? e->d_buf + 2 * off : e->d_ring + (c % kRing) * (e->d_ring_chunk / 4);
         if (!resident) CU(cudaStreamWaitEvent(e->copy_stream, e->ring_free[c % kRing], 0)); // previous tenant consumed?
         if (mp) {
-            const void *from;
-            if (src.pinned) {
-                from = src.img + off * 8;
-            } else {
-                CU(cudaEventSynchronize(e->stage_done[stage])); // staging slot free again?
-                char *sb = (char *)e->h_stage[stage];
-                const u64 base = off * 8;
-                const bool ok = e->pool->parallel(mp * 8, [&](size_t lo, size_t hi) { return src.read(sb + lo, base + lo, hi - lo); });
-                if (!ok) return fail(e, PAPR_ERR_IO, "read failed while streaming the capture");
-                from = sb;
-            }
+            const void *from = src.pinned ? (const void *)(src.img + off * 8) : feeder->wait_filled(c);
+            if (!from) return fail(e, PAPR_ERR_IO, "read failed while streaming the capture");
             CU(cudaMemcpyAsync(dst, from, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
-            if (!src.pinned) {
-                CU(cudaEventRecord(e->stage_done[stage], e->copy_stream));
-                stage = (stage + 1) % kStages;
+            if (feeder) {
+                CU(cudaEventRecord(e->stage_done[c % e->h_stage_slots], e->copy_stream));
+                feeder->issued(c);
             }
             e->h2d += mp * 8;
         }

@@ -307,6 +307,7 @@ def test_exact_sequential_sum_bit_for_bit(built, eng, torch_cuda):
             # many chunks: tile sums / binade placement / tile runs trail the copies chunk by chunk;
             # resident shard, then the re-streaming mode (ring of device chunk buffers, two PCIe passes)
             eng.set("chunk_bytes", 1 << 20)
+            eng.set("staging_threads", 2)  # 4 staging slots: they wrap around several times
             try:
                 for budget in (0, 1 << 20):
                     eng.set("max_resident_bytes", budget)
@@ -315,6 +316,7 @@ def test_exact_sequential_sum_bit_for_bit(built, eng, torch_cuda):
                     assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), False), (name, budget)
             finally:
                 eng.set("max_resident_bytes", 0)
+                eng.set("staging_threads", -1)
                 eng.set("chunk_bytes", 16 << 20)
     finally:
         eng.set("exact_sum", -1)
