@@ -23,7 +23,10 @@
 #include <thread>
 #include <vector>
 
+#include <ctype.h>
 #include <errno.h>
+#include <pthread.h>
+#include <sched.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -1531,6 +1534,39 @@ extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, pa
 
 namespace {
 
+// Bind the calling thread to the CPUs next to a GPU (sysfs local_cpulist of its PCI function), so that
+// the pinned staging slots it allocates and the helper threads it starts live on the GPU's NUMA
+// node.  Best effort: returns false and changes nothing when the topology cannot be read.
+static bool bind_thread_near_device(int device, cpu_set_t *saved)
+{
+    char busid[32] = {0};
+    if (cudaDeviceGetPCIBusId(busid, (int)sizeof(busid), device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char *p = busid; *p; ++p) *p = (char)tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + busid + "/local_cpulist";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    cpu_set_t want;
+    CPU_ZERO(&want);
+    int ncpu = 0;
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET(c, &want); ++ncpu; }
+    }
+    if (ncpu == 0) return false;
+    if (pthread_getaffinity_np(pthread_self(), sizeof(*saved), saved) != 0) return false;
+    cpu_set_t both;
+    CPU_AND(&both, &want, saved); // never widen what the user (taskset, cgroup) allowed
+    if (CPU_COUNT(&both) == 0 || CPU_EQUAL(&both, saved)) return false;
+    return pthread_setaffinity_np(pthread_self(), sizeof(both), &both) == 0;
+}
+
 class Barrier {
 public:
     explicit Barrier(int n) : n_(n), count_(0), gen_(0) {}
@@ -1692,6 +1728,8 @@ static int multi_analyze_source(papr_multi *m, const HostSource &whole, int grap
         const u64 lo = std::min(npairs, (u64)r * per), hi = std::min(npairs, (u64)(r + 1) * per);
         auto step = [&](int rc) { if (rc < 0 && !failed.exchange(true)) { rcs[r] = rc; } return rc; };
         begin_analysis(e);
+        cpu_set_t saved_cpus;
+        const bool bound = N > 1 && bind_thread_near_device(e->device, &saved_cpus);
         // pass 1 while the shard streams in
         cudaSetDevice(e->device);
         if (!failed) step(host_stream_stats(e, whole.slice(lo * 8, (hi - lo) * 8), lo, &ns[r], (tail && r == tail_rank) ? tail_pair : nullptr));
@@ -1758,6 +1796,7 @@ static int multi_analyze_source(papr_multi *m, const HostSource &whole, int grap
         mark(r, "CCDF pass + exchange (rank 0)");
         bar.wait(); // ---- E: counts on the host
         mark(r, "barrier E");
+        if (bound) pthread_setaffinity_np(pthread_self(), sizeof(saved_cpus), &saved_cpus);
     };
     std::vector<std::thread> th;
     for (int r = 1; r < N; ++r) th.emplace_back(rank_main, r);
