@@ -45,6 +45,8 @@ constexpr int kSeqLagRing = 3;             // chunks between a chunk's tile sums
 constexpr int kSeqLagResident = 6;         // ... and when nothing limits how far the copies run ahead (< kSeqEvents)
 constexpr int kSeqEvents = 8;
 constexpr size_t kTileBytes = (size_t)PAPR_SEQ_TILE * 8; // chunks are whole tiles of the exact-sum emulation
+constexpr size_t kPieceBytes = 8u << 20;   // staging granularity: small enough to still sit in the host's
+                                           // last-level cache when the DMA engine reads it back
 constexpr u64 kMaxLaunchSamples = 1ull << 31;  // per scan launch (32-bit sample offsets inside a launch)
 constexpr int kLevels1dB = 256;            // table sizes: PAPR < 192.7 dB (papr_b200.h)
 constexpr int kLevelsGraph = PAPR_MAX_LEVELS;
@@ -198,7 +200,7 @@ struct papr_engine {
     int mode = PAPR_MODE_AUTO;
     int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
-    size_t chunk_bytes = 16u << 20; // measured on the file path: 16 MiB chunks stay in the host LLC
+    size_t chunk_bytes = 64u << 20; // H2D + kernel granularity; pageable / file sources are staged in 8 MiB pieces
     int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16]
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
@@ -1116,15 +1118,24 @@ static int staging_threads_of(const papr_engine *e)
     return std::min(kMaxStages - 2, std::max(1, n));
 }
 
-// one pinned slot per helper thread plus two, so that a copy can be in flight while every helper reads
+static size_t piece_bytes_of(const papr_engine *e)
+{
+    size_t p = std::min(kPieceBytes, e->chunk_bytes);
+    while (e->chunk_bytes % p) p >>= 1; // chunk_bytes is a multiple of 256 KiB, so this stops there at the latest
+    return p;
+}
+
+// one pinned slot (one staging piece) per helper thread plus two, so that a copy can be in flight
+// while every helper reads
 static int ensure_staging(papr_engine *e)
 {
     const int slots = staging_threads_of(e) + 2;
-    if (e->h_stage_bytes != e->chunk_bytes || e->h_stage_slots != slots) {
+    const size_t piece = piece_bytes_of(e);
+    if (e->h_stage_bytes != piece || e->h_stage_slots != slots) {
         for (auto &p : e->h_stage) { if (p) cudaFreeHost(p); p = nullptr; }
         e->h_stage_bytes = 0;
-        for (int i = 0; i < slots; ++i) CU(cudaHostAlloc(&e->h_stage[i], e->chunk_bytes, cudaHostAllocDefault));
-        e->h_stage_bytes = e->chunk_bytes;
+        for (int i = 0; i < slots; ++i) CU(cudaHostAlloc(&e->h_stage[i], piece, cudaHostAllocDefault));
+        e->h_stage_bytes = piece;
         e->h_stage_slots = slots;
     }
     return PAPR_OK;
@@ -1196,25 +1207,29 @@ static int stream_chunks(papr_engine *e, const HostSource &src, const StreamGeom
         if (!resident) cudaEventRecord(e->ring_free[c % kRing], e->stream);
     };
     std::unique_ptr<ChunkFeeder> feeder; // helper threads stop and join when this goes out of scope
+    const u64 piece = piece_bytes_of(e);
     if (!src.pinned && g.npairs)
-        feeder.reset(new ChunkFeeder(e->device, src, (g.npairs + g.chunk_samples - 1) / g.chunk_samples, e->chunk_bytes,
-                                     g.npairs * 8, staging_threads_of(e), e->h_stage, e->stage_done, e->h_stage_slots));
+        feeder.reset(new ChunkFeeder(e->device, src, (g.npairs * 8 + piece - 1) / piece, piece, g.npairs * 8,
+                                     staging_threads_of(e), e->h_stage, e->stage_done, e->h_stage_slots));
     u64 c = 0;
     for (u64 off = 0; off < g.n; off += g.chunk_samples, ++c) {
         const u64 m = std::min(g.chunk_samples, g.n - off);               // samples of this chunk (incl. the tail sample)
         const u64 mp = std::min(m, g.npairs > off ? g.npairs - off : 0);  // complete pairs to copy from the source
         float *dst = resident ? e->d_buf + 2 * off : e->d_ring + (c % kRing) * (e->d_ring_chunk / 4);
         if (!resident) CU(cudaStreamWaitEvent(e->copy_stream, e->ring_free[c % kRing], 0)); // previous tenant consumed?
-        if (mp) {
-            const void *from = src.pinned ? (const void *)(src.img + off * 8) : feeder->wait_filled(c);
-            if (!from) return fail(e, PAPR_ERR_IO, "read failed while streaming the capture");
-            CU(cudaMemcpyAsync(dst, from, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
-            if (feeder) {
-                CU(cudaEventRecord(e->stage_done[c % e->h_stage_slots], e->copy_stream));
-                feeder->issued(c);
+        if (mp && src.pinned) {
+            CU(cudaMemcpyAsync(dst, src.img + off * 8, mp * 8, cudaMemcpyHostToDevice, e->copy_stream));
+        } else if (mp) { // piece by piece through the staging slots (chunks are whole pieces)
+            for (u64 b = 0; b < mp * 8; b += piece) {
+                const u64 p = (off * 8 + b) / piece;
+                const void *from = feeder->wait_filled(p);
+                if (!from) return fail(e, PAPR_ERR_IO, "read failed while streaming the capture");
+                CU(cudaMemcpyAsync((char *)dst + b, from, std::min(piece, mp * 8 - b), cudaMemcpyHostToDevice, e->copy_stream));
+                CU(cudaEventRecord(e->stage_done[p % e->h_stage_slots], e->copy_stream));
+                feeder->issued(p);
             }
-            e->h2d += mp * 8;
         }
+        e->h2d += mp * 8;
         if (g.tail && off + m == g.n) {
             CU(cudaMemcpyAsync(dst + 2 * (g.npairs - off), g.tail_pair, 8, cudaMemcpyHostToDevice, e->copy_stream));
             e->h2d += 8;
@@ -1388,8 +1403,9 @@ static int analyze_source(papr_engine *e, const HostSource &src, int graph, papr
     if (resident) rc = ensure_device_buffer(e, g.n * 8 + 16);
     else rc = ensure_ring(e);
     if (rc) return rc;
+    mark(resident ? "device buffer (resident shard)" : "device buffers (re-streaming ring)");
     if (!src.pinned && g.npairs && (rc = ensure_staging(e))) return rc;
-    mark(resident ? "buffers (resident shard)" : "buffers (re-streaming ring)");
+    mark("pinned staging slots");
     CU(cudaEventRecord(e->ev_begin, e->stream));
     bool exact_done = false;
     if ((rc = host_pass1(e, src, g, resident, e->exact_sum != 0, &exact_done))) return rc;

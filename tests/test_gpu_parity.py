@@ -65,7 +65,7 @@ def test_host_buffer_path_equals_reference(built, eng, name, graph, manifest):
     for chunk in (64 << 20, 1 << 20):  # one chunk / many chunks (+ the staging ring wrapping around)
         eng.set("chunk_bytes", chunk)
         assert built.format_result(eng.analyze_host(img, graph=graph)) == _gold(name, graph)
-    eng.set("chunk_bytes", 16 << 20)
+    eng.set("chunk_bytes", 64 << 20)
 
 
 @pytest.mark.parametrize("mode", [1, 2], ids=["two_pass", "fused"])
@@ -104,7 +104,7 @@ def test_capture_larger_than_hbm_is_restreamed(built, eng, name, graph, manifest
         assert built.format_result(eng.analyze_file(str(path), graph)) == _gold(name, graph)
     finally:
         eng.set("max_resident_bytes", 0)
-        eng.set("chunk_bytes", 16 << 20)
+        eng.set("chunk_bytes", 64 << 20)
 
 
 def test_pinned_source_goes_direct(built, eng, torch_cuda):
@@ -317,7 +317,7 @@ def test_exact_sequential_sum_bit_for_bit(built, eng, torch_cuda):
             finally:
                 eng.set("max_resident_bytes", 0)
                 eng.set("staging_threads", -1)
-                eng.set("chunk_bytes", 16 << 20)
+                eng.set("chunk_bytes", 64 << 20)
     finally:
         eng.set("exact_sum", -1)
         eng.set("mode", 0)

@@ -15,9 +15,9 @@ pinned.copy_(d)
 torch.cuda.synchronize()
 del d
 torch.cuda.empty_cache()
-for label, knobs in (("default", {}), ("chunk 64 MiB", {"chunk_bytes": 64 << 20}), ("chunk 4 MiB", {"chunk_bytes": 4 << 20}),
+for label, knobs in (("default", {}), ("chunk 16 MiB", {"chunk_bytes": 16 << 20}), ("chunk 256 MiB", {"chunk_bytes": 256 << 20}),
                      ("exact_sum off", {"exact_sum": 0}), ("default again", {})):
-    eng.set("chunk_bytes", 16 << 20)
+    eng.set("chunk_bytes", 64 << 20)
     eng.set("exact_sum", -1)
     for k, v in knobs.items():
         eng.set(k, v)
