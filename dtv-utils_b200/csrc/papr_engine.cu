@@ -213,6 +213,8 @@ struct papr_engine {
     u64 *d_tile_run = nullptr, *h_tile_run = nullptr;
     float *h_tile_data = nullptr;
     unsigned seq_dirty = 0;
+    const float *seq_sums_ptr = nullptr; // h_tile_sum currently holds the tile sums of this resident shard ...
+    u64 seq_sums_n = 0;                  // ... of this many samples (computed under the H2D shadow)
     // device work buffers
     int grid = 0;
     DevWork *d_work = nullptr;
@@ -547,6 +549,7 @@ static void begin_analysis(papr_engine *e)
     e->scan_pairs = 0;
     e->launches = 0;
     e->h2d = e->d2h = 0;
+    e->seq_sums_ptr = nullptr;
     cudaSetDevice(e->device);
 }
 
@@ -666,6 +669,7 @@ static int seq_tile_sums(papr_engine *e, const float *d_iq, u64 n)
 {
     const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
     int rc;
+    if (ntiles && e->seq_sums_ptr == d_iq && e->seq_sums_n == n) return PAPR_OK; // already computed while streaming in
     if ((rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
     if (ntiles == 0) return PAPR_OK;
     papr_launch_tilesum(d_iq, n, e->d_tile_sum, e->num_sms * 2, e->stream);
@@ -1264,13 +1268,16 @@ static TileFetch tile_fetcher(papr_engine *e, const HostSource &src, const Strea
 // GPU while later chunks are still crossing PCIe; the host chains them at the end).  On return the
 // local state is finalized in d_out->local (sum already exact if *exact_done) - nothing synchronised
 // unless inline_exact.
-static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, bool inline_exact,
+enum SeqInline { SEQ_NONE = 0, SEQ_SUMS_ONLY = 1, SEQ_FULL = 2 };
+
+static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, SeqInline seq,
                       bool *exact_done)
 {
     int rc;
     *exact_done = false;
+    const bool inline_exact = seq == SEQ_FULL;
     const u64 ntiles = (g.n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
-    if (inline_exact && (rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
+    if (seq != SEQ_NONE && (rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
     if ((rc = enqueue_reset(e))) return rc;
 
     struct Pending { const float *d; u64 off, m, c; };
@@ -1297,13 +1304,14 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
     rc = stream_chunks(e, src, g, resident, [&](const float *d, u64 off, u64 m, u64 c, bool last, const ChunkRelease &release) -> int {
         int r = enqueue_scan(e, true, false, d, m, g.first + off, false);
         if (r) return r;
-        if (!inline_exact) { release(c); return PAPR_OK; }
+        if (seq == SEQ_NONE) { release(c); return PAPR_OK; }
         const u64 tile0 = off / PAPR_SEQ_TILE, nt = (m + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
         papr_launch_tilesum(d, m, e->d_tile_sum + tile0, (int)std::min<u64>((u64)e->num_sms * 2, nt), e->stream);
         e->launches += 1;
         CU(cudaMemcpyAsync(e->h_tile_sum + tile0, e->d_tile_sum + tile0, nt * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaEventRecord(e->seq_ev[c % kSeqEvents], e->stream));
         e->d2h += nt * 8;
+        if (seq == SEQ_SUMS_ONLY) { release(c); return PAPR_OK; } // the caller classifies and chains across shards
+        CU(cudaEventRecord(e->seq_ev[c % kSeqEvents], e->stream));
         pend.push_back({d, off, m, c});
         while (pend.size() - pend_head > (size_t)(last ? 0 : (resident ? kSeqLagResident : kSeqLagRing)))
             if ((r = process(pend[pend_head++], release))) return r;
@@ -1408,7 +1416,7 @@ static int analyze_source(papr_engine *e, const HostSource &src, int graph, papr
     mark("pinned staging slots");
     CU(cudaEventRecord(e->ev_begin, e->stream));
     bool exact_done = false;
-    if ((rc = host_pass1(e, src, g, resident, e->exact_sum != 0, &exact_done))) return rc;
+    if ((rc = host_pass1(e, src, g, resident, e->exact_sum != 0 ? SEQ_FULL : SEQ_NONE, &exact_done))) return rc;
     mark("H2D + pass 1 (+ exact sum)");
     // local state -> merged state, avg, L, levels on the device
     papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
@@ -1465,8 +1473,13 @@ static int host_stream_stats(papr_engine *e, const HostSource &src, u64 first, u
         return fail(e, PAPR_ERR_ARG, "shard exceeds the resident budget of this GPU: use more shards");
     if ((rc = ensure_device_buffer(e, g.n * 8 + 16))) return rc;
     if (!src.pinned && g.npairs && (rc = ensure_staging(e))) return rc;
+    // tile sums of the sequential-sum emulation ride along under the H2D shadow; the caller places and
+    // chains the tiles across shards afterwards (papr_seqsum_* / papr_multi), once it has synchronised
     bool exact_done = false;
-    return host_pass1(e, src, g, true, false, &exact_done);
+    const bool sums = e->exact_sum != 0 && g.n > 0;
+    if ((rc = host_pass1(e, src, g, true, sums ? SEQ_SUMS_ONLY : SEQ_NONE, &exact_done))) return rc;
+    if (sums) { e->seq_sums_ptr = e->d_buf; e->seq_sums_n = g.n; }
+    return PAPR_OK;
 }
 
 // Sharded callers with host-resident shards: pass 1 while streaming in; the shard stays resident at
