@@ -353,7 +353,7 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (e->h_tile_data) cudaFreeHost(e->h_tile_data);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
     if (e->h_out) cudaFreeHost(e->h_out);
-    for (auto &p : e->h_stage) if (p) cudaFreeHost(p);
+    if (e->h_stage[0]) cudaFreeHost(e->h_stage[0]);
     for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ring_free) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->seq_ev) if (ev) cudaEventDestroy(ev);
@@ -710,7 +710,7 @@ static int seq_tile_runs(papr_engine *e, const float *d_iq, u64 n)
     const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
     if (ntiles == 0) return PAPR_OK;
     CU(cudaMemcpyAsync(e->d_tile_code, e->h_tile_code, ntiles * sizeof(short), cudaMemcpyHostToDevice, e->stream));
-    papr_launch_seqsum(d_iq, n, e->d_tile_code, e->d_tile_run, e->num_sms, e->stream);
+    papr_launch_seqsum(d_iq, n, e->d_tile_code, e->d_tile_run, (int)std::min<u64>((u64)e->num_sms * 8, ntiles), e->stream);
     CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->launches += 1;
@@ -1136,9 +1136,12 @@ static int ensure_staging(papr_engine *e)
     const int slots = staging_threads_of(e) + 2;
     const size_t piece = piece_bytes_of(e);
     if (e->h_stage_bytes != piece || e->h_stage_slots != slots) {
-        for (auto &p : e->h_stage) { if (p) cudaFreeHost(p); p = nullptr; }
+        if (e->h_stage[0]) cudaFreeHost(e->h_stage[0]); // one allocation, carved into the slots
+        for (auto &p : e->h_stage) p = nullptr;
         e->h_stage_bytes = 0;
-        for (int i = 0; i < slots; ++i) CU(cudaHostAlloc(&e->h_stage[i], piece, cudaHostAllocDefault));
+        void *block = nullptr;
+        CU(cudaHostAlloc(&block, piece * (size_t)slots, cudaHostAllocDefault));
+        for (int i = 0; i < slots; ++i) e->h_stage[i] = (char *)block + piece * (size_t)i;
         e->h_stage_bytes = piece;
         e->h_stage_slots = slots;
     }
@@ -1294,7 +1297,7 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
             CU(cudaMemcpyAsync(e->d_tile_code + tile0, e->h_tile_code + tile0, nt * sizeof(short), cudaMemcpyHostToDevice,
                                e->stream));
             papr_launch_seqsum(ch.d, ch.m, e->d_tile_code + tile0, e->d_tile_run + 2 * tile0,
-                               (int)std::min<u64>((u64)e->num_sms, nt), e->stream);
+                               (int)std::min<u64>((u64)e->num_sms * 8, nt), e->stream);
             e->launches += 1;
             e->h2d += nt * 2;
         }

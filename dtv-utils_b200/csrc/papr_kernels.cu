@@ -936,74 +936,90 @@ __device__ __forceinline__ SeqRun seq_compose(const SeqRun &a, const SeqRun &b)
     return c;
 }
 
-// one CTA per tile of PAPR_SEQ_TILE samples; thread t owns the 32 consecutive samples t*32..t*32+31
-__global__ void __launch_bounds__(1024) papr_seqsum_kernel(const float *iq, u64 nsamples, const short *tile_code,
+// One sample's effect on the two candidate states (even / odd entry), papr.c:104 in integer form.
+__device__ __forceinline__ void seq_step(float v, int U, u64 &d0, u64 &d1)
+{
+    const unsigned b = __float_as_uint(v);
+    if (b == 0) return;
+    const unsigned e = b >> 23;
+    const unsigned M = e ? ((b & 0x7fffffu) | 0x800000u) : (b & 0x7fffffu); // v = M * 2^E
+    const int E = (int)(e ? e : 1u) - 150;
+    const int shift = U - E;
+    if (shift <= 0) {            // v is a whole number of ulps: exact add
+        const u64 q = (u64)M << (-shift);
+        d0 += q; d1 += q;
+    } else if (shift <= 24) {    // q ulps plus a fraction f = rem / 2^shift
+        const u64 q = M >> shift;
+        const unsigned rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
+        u64 r0 = 0, r1 = 0;
+        if (rem > half) { r0 = 1; r1 = 1; }
+        else if (rem == half) { r0 = (d0 + q) & 1; r1 = (1 + d1 + q) & 1; } // tie: to even
+        d0 += q + r0; d1 += q + r1;
+    }                            // shift >= 25: f < 1/2 and q = 0, the add rounds back
+}
+
+// One CTA of SEQ_T threads per tile of PAPR_SEQ_TILE samples; thread t owns the SEQ_PER consecutive
+// samples t*SEQ_PER.. of the tile and walks them in file order straight from global memory (16-byte
+// loads, 4 in flight; the two halves of every 32-byte sector are consumed back to back), then the
+// threads' runs are composed in thread (= file) order: shuffles inside a warp, one pass over the
+// warps.  Several CTAs per SM are resident, each in a different phase, which hides the latency.
+#define SEQ_T 256
+#define SEQ_PER (PAPR_SEQ_TILE / SEQ_T) // 128 samples = 1 KiB per thread
+__global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64 nsamples, const short *tile_code,
                                                            SeqRun *tile_run)
 {
-    extern __shared__ __align__(16) unsigned char seq_smem[];
-    float *s_v = reinterpret_cast<float *>(seq_smem);      // [1024][33]: row t = the samples of thread t
-    SeqRun *s_run = reinterpret_cast<SeqRun *>(seq_smem);  // reused for the ordered composition
+    __shared__ SeqRun s_w[SEQ_T / 32];
     const unsigned ntiles = (unsigned)((nsamples + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE);
-    const float4 *p = reinterpret_cast<const float4 *>(iq);
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int k = tile_code[tile];
         if (k >= PAPR_SEQ_ZERO) continue; // zero or dirty tile: nothing to do here (uniform per CTA)
-        const u64 s0 = (u64)tile * PAPR_SEQ_TILE;
-        for (int j = 0; j < PAPR_SEQ_TILE / 2 / 1024; ++j) {
-            const unsigned f4 = t + 1024u * j;
-            const u64 s = s0 + 2ull * f4;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s + 1 < nsamples) q = ldg_stream(p + (s >> 1));
-            else if (s < nsamples) { float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s); q.x = h.x; q.y = h.y; }
-            const unsigned pos = 2u * f4;
-            float *dst = s_v + (pos >> 5) * 33 + (pos & 31);
-            dst[0] = power_of(q.x, q.y);
-            dst[1] = power_of(q.z, q.w);
-        }
-        __syncthreads();
-        const int U = k - 52; // exponent of the binade's ulp
+        const int U = k - 52;             // exponent of the binade's ulp
+        const u64 s0 = (u64)tile * PAPR_SEQ_TILE + (u64)t * SEQ_PER;
+        const float4 *p = reinterpret_cast<const float4 *>(iq + 2 * s0);
         u64 d0 = 0, d1 = 0;
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-            const unsigned b = __float_as_uint(s_v[t * 33 + i]);
-            if (b == 0) continue;
-            const unsigned e = b >> 23;
-            const unsigned M = e ? ((b & 0x7fffffu) | 0x800000u) : (b & 0x7fffffu); // v = M * 2^E
-            const int E = (int)(e ? e : 1u) - 150;
-            const int shift = U - E;
-            if (shift <= 0) {            // v is a whole number of ulps: exact add
-                const u64 q = (u64)M << (-shift);
-                d0 += q; d1 += q;
-            } else if (shift <= 24) {    // q ulps plus a fraction f = rem / 2^shift
-                const u64 q = M >> shift;
-                const unsigned rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
-                u64 r0 = 0, r1 = 0;
-                if (rem > half) { r0 = 1; r1 = 1; }
-                else if (rem == half) { r0 = (d0 + q) & 1; r1 = (1 + d1 + q) & 1; } // tie: to even
-                d0 += q + r0; d1 += q + r1;
-            }                            // shift >= 25: f < 1/2 and q = 0, the add rounds back
+        if (s0 + SEQ_PER <= nsamples) {
+#pragma unroll 1
+            for (int j = 0; j < SEQ_PER / 2; j += 4) {
+                float4 q[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) q[u] = __ldg(p + j + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    seq_step(power_of(q[u].x, q[u].y), U, d0, d1);
+                    seq_step(power_of(q[u].z, q[u].w), U, d0, d1);
+                }
+            }
+        } else { // ragged end of the capture
+            for (u64 s = s0; s < nsamples && s < s0 + SEQ_PER; ++s) {
+                const float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s);
+                seq_step(power_of(h.x, h.y), U, d0, d1);
+            }
         }
-        __syncthreads();
-        s_run[t].d0 = d0; s_run[t].d1 = d1;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) { // ordered tree: thread t (multiple of 2o) <- t then t+o
-            if ((t & (2 * o - 1)) == 0) s_run[t] = seq_compose(s_run[t], s_run[t + o]);
-            __syncthreads();
+        SeqRun r;
+        r.d0 = d0; r.d1 = d1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { // ordered: lane l (multiple of 2o) <- l then l+o
+            SeqRun nb;
+            nb.d0 = __shfl_down_sync(FULL, r.d0, o);
+            nb.d1 = __shfl_down_sync(FULL, r.d1, o);
+            r = seq_compose(r, nb); // only the lanes that are multiples of 2o keep a meaningful value
         }
-        if (t == 0) tile_run[tile] = s_run[0];
+        if (lane == 0) s_w[warp] = r;
+        __syncthreads();
+        if (t == 0) {
+            SeqRun acc = s_w[0];
+            for (int w = 1; w < SEQ_T / 32; ++w) acc = seq_compose(acc, s_w[w]);
+            tile_run[tile] = acc;
+        }
         __syncthreads();
     }
 }
 
-int papr_seqsum_configure(void)
-{
-    return cudaFuncSetAttribute(papr_seqsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4) ==
-                   cudaSuccess ? 0 : -1;
-}
+int papr_seqsum_configure(void) { return 0; } // no dynamic shared memory any more
 
 void papr_launch_seqsum(const float *iq, u64 nsamples, const short *tile_code, void *tile_run, int grid,
                         cudaStream_t s)
 {
-    papr_seqsum_kernel<<<grid, 1024, 1024 * 33 * 4, s>>>(iq, nsamples, tile_code, reinterpret_cast<SeqRun *>(tile_run));
+    papr_seqsum_kernel<<<grid, SEQ_T, 0, s>>>(iq, nsamples, tile_code, reinterpret_cast<SeqRun *>(tile_run));
 }

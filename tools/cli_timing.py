@@ -38,12 +38,7 @@ try:
     print(r1.stderr.decode(), flush=True)
     run({}, [], "1dB warm")
     run({"PAPR_B200_EXACT_SUM": "0"}, [], "1dB exact_sum=0")
-    for th in (8, 16, 32):
-        run({"PAPR_B200_STAGING_THREADS": str(th)}, [], f"1dB threads={th}")
-    for mb in (16, 256):
-        run({"PAPR_B200_CHUNK_MB": str(mb)}, [], f"1dB chunk={mb}MB")
     run({"PAPR_B200_MAX_RESIDENT_MB": "1024"}, [], "1dB re-streamed (1 GiB budget)")
-    run({"PAPR_B200_MAX_RESIDENT_MB": "1024", "PAPR_B200_TRACE": "1"}, ["-g"], "-g re-streamed")
     rg = run({}, ["-g"], "-g")
     # the reference on the first 1 GiB (2^27 samples)
     head = "/dev/shm/papr_cli_timing_head.cfile"
