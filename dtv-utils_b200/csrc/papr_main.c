@@ -19,6 +19,18 @@ static double now_ms(void)
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+/* papr.c:132-135,154-161 / 186-190: the text goes out as soon as the numbers exist, before the GPU
+ * resources (a resident copy of the capture among them) are torn down */
+static void print_result(const papr_result *r)
+{
+    size_t cap = 256 + (size_t)r->nlevels * 64 + 1024;
+    char *text = (char *)malloc(cap);
+    long len = text ? papr_format(r, text, cap) : -1;
+    if (len > 0) fwrite(text, 1, (size_t)len, stdout);
+    fflush(stdout);
+    free(text);
+}
+
 static void usage(void)
 {
     fprintf(stderr, "usage: papr -g <infile>\n"); /* papr.c:54-56, 86-88 */
@@ -93,6 +105,7 @@ int papr_main(int argc, char **argv)
         if (getenv("PAPR_B200_STATS"))
             fprintf(stderr, "papr_b200: %d shards, exchange=%s, wall_ms=%.3f launches=%u h2d=%llu\n", ndev,
                     papr_multi_exchange(m), r->device_ms, r->kernel_launches, (unsigned long long)r->h2d_bytes);
+        print_result(r);
         papr_multi_destroy(m);
     } else {
         papr_engine *e = NULL;
@@ -119,13 +132,9 @@ int papr_main(int argc, char **argv)
         if (getenv("PAPR_B200_STATS"))
             fprintf(stderr, "papr_b200: create_ms=%.1f analyze_ms=%.1f device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n",
                     t1 - t0, t2 - t1, r->device_ms, r->scan_ms, r->kernel_launches, (unsigned long long)r->h2d_bytes);
+        print_result(r);
         papr_engine_destroy(e);
     }
-    size_t cap = 256 + (size_t)r->nlevels * 64 + 1024;
-    char *text = (char *)malloc(cap);
-    long len = papr_format(r, text, cap);
-    if (len > 0) fwrite(text, 1, (size_t)len, stdout);
-    free(text);
     free(r);
     return 0;
 }
