@@ -50,7 +50,9 @@ eng = pb.Engine(int(os.environ["LOCAL_RANK"]))
 n = (1 << 22) + 4096            # per rank; ragged vs the 256-sample batch on purpose (+4096 keeps 16 B alignment)
 d = torch.empty(2 * n, dtype=torch.float32, device="cuda")
 eng.siggen(d, rank * n, n, 5)
+import struct
 whole = oracle_binding.siggen(0, world * n, 5)
+seq_sum = oracle_binding.analyze(whole, False)[0].sum
 ok = True
 for graph in (False, True):
     want = oracle_binding.run_image(whole.tobytes(), graph)
@@ -60,6 +62,10 @@ for graph in (False, True):
     pinned = d.cpu().pin_memory()
     res = pb.analyze_sharded(eng, None, n, rank * n, graph, host_image=pinned)
     ok &= pb.format_result(res) == want
+    # host-resident shards chain the reference's sequential sum across the ranks: bit for bit
+    ok &= struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
+    res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2, exact_sum=True)  # and on request for resident ones
+    ok &= pb.format_result(res) == want and struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
 print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
