@@ -107,6 +107,33 @@ def test_capture_larger_than_hbm_is_restreamed(built, eng, name, graph, manifest
         eng.set("chunk_bytes", 64 << 20)
 
 
+def test_chunk_boundary_cases_all_sources(built, eng, torch_cuda, tmp_path):
+    """Captures whose length sits exactly on / just past a chunk boundary (1 MiB chunks = 131072 samples):
+    a last chunk that holds nothing but the lone-I tail sample, ragged trailing bytes, more chunks than
+    staging slots and ring slots - through every source (pageable image, pinned image, file) and both
+    residency modes, against the oracle."""
+    from test_oracle import edge_images
+    eng.set("chunk_bytes", 1 << 20)
+    eng.set("staging_threads", 2)
+    try:
+        for k, nf, img in edge_images():
+            path = tmp_path / ("edge%d.cfile" % k)
+            path.write_bytes(img)
+            pinned = torch_cuda.from_numpy(np.frombuffer(img[: len(img) // 4 * 4], np.float32).copy()).pin_memory()
+            for graph in (False, True):
+                want = oracle_binding.run_image(img, graph)
+                for budget in (0, 1 << 20):
+                    eng.set("max_resident_bytes", budget)
+                    assert built.format_result(eng.analyze_host(img, graph=graph)) == want, (nf, graph, budget, "image")
+                    assert built.format_result(eng.analyze_file(str(path), graph)) == want, (nf, graph, budget, "file")
+                    if len(img) % 4 == 0:  # a pinned tensor cannot carry the ragged bytes
+                        assert built.format_result(eng.analyze_host(pinned, graph=graph)) == want, (nf, graph, budget, "pinned")
+    finally:
+        eng.set("max_resident_bytes", 0)
+        eng.set("staging_threads", -1)
+        eng.set("chunk_bytes", 64 << 20)
+
+
 def test_pinned_source_goes_direct(built, eng, torch_cuda):
     f = torch_cuda.from_numpy(fixtures.siggen(0, 300_000, 11)).pin_memory()
     res = eng.analyze_host(f, graph=True)

@@ -106,6 +106,10 @@ def test_virtual_shards_single_process_all_fixtures(built, manifest, nshards):
                 want = open(os.path.join(GOLD, name + (".g.out" if graph else ".out")), "rb").read()
                 res = m.analyze_host(img, graph=graph)
                 assert built.format_result(res) == want, (name, graph)
+        from test_oracle import edge_images
+        for k, nf, img in edge_images():  # lengths on / just past a chunk (= shard) boundary, ragged bytes
+            for graph in (False, True):
+                assert built.format_result(m.analyze_host(img, graph=graph)) == oracle_binding.run_image(img, graph), (nf, graph)
         f = fixtures.siggen(0, 900_001, 31)  # sum chained across 3 shards == the oracle's sequential sum
         st, *_ = oracle_binding.analyze(f, False)
         res = m.analyze_host(f)

@@ -54,3 +54,27 @@ def test_reference_binary_if_present(manifest, tmp_path):
         for graph in (False, True):
             r = subprocess.run([ref] + (["-g"] if graph else []) + [str(p)], capture_output=True)
             assert r.stdout == _gold(name, graph)
+
+
+def edge_images():
+    """Captures whose length sits on / just past a multiple of 131072 samples (the 1 MiB chunks the GPU
+    tests force), with 0-3 ragged trailing bytes; shared with tests/test_gpu_parity.py."""
+    cs = 131072
+    base = fixtures.siggen(0, 6 * cs + 10, 77)
+    for k, nf in enumerate([2 * cs, 2 * cs + 1, 4 * cs + 1, 2 * (5 * cs) + 1, 2 * (6 * cs) + 3, 2 * cs - 1, 1, 2]):
+        yield k, nf, base[:nf].tobytes() + bytes([1, 2, 3][: k % 4])
+
+
+def test_oracle_equals_reference_binary_on_chunk_boundary_captures(tmp_path):
+    """The GPU edge-case test checks against the oracle; this pins the oracle itself to the unmodified
+    reference binary on the same captures (lone-I tails paired with stale Q, ragged bytes)."""
+    import subprocess
+    ref = os.path.join(oracle_binding.ORACLE_DIR, "_ref", "papr")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/papr not built")
+    for k, nf, img in edge_images():
+        p = tmp_path / ("edge%d.cfile" % k)
+        p.write_bytes(img)
+        for graph in (False, True):
+            r = subprocess.run([ref] + (["-g"] if graph else []) + [str(p)], capture_output=True)
+            assert r.stdout == oracle_binding.run_image(img, graph), (k, nf, graph)
