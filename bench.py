@@ -328,7 +328,9 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": t_rank / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, n), mode=("fused" if res.mode_used == 2 else "two_pass"),
-                               parallelism="byte-range x%d" % world),
+                               parallelism="byte-range x%d" % world,
+                               exchange=("none (single shard)" if world == 1 else
+                                         "in-kernel over NVLink peer memory" if getattr(eng, "_p2p", False) else "nccl")),
                 "hbm_gbs": value * BYTES_PER_SAMPLE, "hbm_pct_of_8tbs": value * BYTES_PER_SAMPLE / 8000 * 100,
                 "device_ms_per_step": dev_ms / args.steps, "event_ms_per_step": ev_ms / args.steps,
                 "roofline": {"bound": "hbm", "kernel": "papr_scan_kernel<stats,hist>" if res.mode_used == 2

@@ -62,7 +62,7 @@ struct PaprPlan {
     int status;         // PLAN_HIST: cell histogram valid; PLAN_BSEARCH: generic kernel must run instead
     int levels_covered; // fused mode: levels whose window fits the cell range / fine table
     float window;       // fused mode: relative half-width of the threshold windows
-    int pad;
+    int pad;            // peer-memory exchange: 1 = a peer's publication did not arrive in time
     double avg_pred;    // fused mode: predicted mean power
 };
 
@@ -91,6 +91,30 @@ struct PaprScanArgs {
     unsigned long long *g_over;    // samples above the cell range
 };
 
+// ---- peer-memory exchange between the ranks of one box (NVLink, cudaIpc-mapped windows) -----------
+// Every GPU owns one window; slot q of it is written by rank q (its stores travel over NVLink),
+// flag[k][q] carries the sequence number of rank q's latest publication of kind k.  The three
+// latency-sized exchanges of a sharded analysis happen INSIDE the kernels that produce / consume
+// the values: publish to every peer's window, release-store the flag, acquire-poll the own window.
+#define PAPR_XCHG_MAX_RANKS 16
+enum { XK_PRE = 0, XK_STATS = 1, XK_COUNTS = 2 };
+
+struct PaprXchgSlot {
+    double pre[4];                                   // presample {sum, sum of squares, count, -}
+    PaprDevStats stats;                              // pass-1 state of the shard
+    unsigned long long counts[PAPR_MAX_LEVELS + 1];  // level counts + status word
+};
+
+struct PaprXchg {
+    unsigned long long flag[3][PAPR_XCHG_MAX_RANKS];
+    PaprXchgSlot slot[PAPR_XCHG_MAX_RANKS];
+};
+
+struct PaprPeers {
+    PaprXchg *win[PAPR_XCHG_MAX_RANKS]; // win[rank] = the local window, the others are peer mappings
+    int rank, world;
+};
+
 // launchers (papr_kernels.cu)
 struct PaprTables {
     const double *pow10;     // [PAPR_MAX_LEVELS] pow(10, x_j) with the host libm, x_j per papr.c:139 / 170-172
@@ -110,7 +134,7 @@ void papr_launch_presample(const float *iq, unsigned long long nsamples, int str
                            double *cta_pre /* [grid*3] */, cudaStream_t s);
 void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s);
 void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas,
-                           int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
+                           float bias, int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
 void papr_launch_plan_exact(const PaprDevLevels *lv, const PaprDevStats *merged, int fine_bytes_log2,
                             PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
 void papr_launch_zero_fine(const PaprPlan *plan, unsigned long long *g_fine, int grid, cudaStream_t s);
@@ -131,5 +155,13 @@ void papr_launch_tilesum(const float *iq, unsigned long long nsamples, double *t
 void papr_launch_seqsum(const float *iq, unsigned long long nsamples, const short *tile_code,
                         void *tile_run /* {u64 d0, d1}[ntiles] */, int grid, cudaStream_t s);
 int papr_seqsum_configure(void);
+void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
+                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, unsigned long long seq, cudaStream_t s);
+void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
+                                   PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
+                                   unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,
+                                   unsigned long long seq, cudaStream_t s);
+void papr_launch_counts_x(unsigned long long *counts, PaprPlan *plan, PaprPeers pp, unsigned long long seq,
+                          cudaStream_t s);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

@@ -201,6 +201,7 @@ struct papr_engine {
     int mode = PAPR_MODE_AUTO;
     int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
+    float predict_bias = 1.0f; // test hook: scales the predicted mean of the fused mode (a wrong one must be caught)
     size_t chunk_bytes = 64u << 20; // H2D + kernel granularity; pageable / file sources are staged in 4 MiB pieces
     int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16]
     int grid_per_sm = 1;
@@ -241,6 +242,11 @@ struct papr_engine {
     cudaEvent_t seq_ev[kSeqEvents] = {};
     u64 max_resident_bytes = 0; // 0 = whatever cudaMemGetInfo leaves after a 1 GiB reserve
     bool streamed = false;      // the last host-path analysis ran in re-streaming mode
+    // peer-memory exchange (one process per GPU): own window + cudaIpc mappings of the other ranks'
+    PaprXchg *d_xchg = nullptr;
+    PaprPeers peers = {};
+    bool xchg_attached = false;
+    u64 xseq[3] = {0, 0, 0};
     // timing / accounting
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_scan[4] = {nullptr, nullptr, nullptr, nullptr};
     int scan_pairs = 0;
@@ -359,6 +365,10 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     for (auto &ev : e->ring_free) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->seq_ev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_ring);
+    if (e->xchg_attached)
+        for (int q = 0; q < e->peers.world; ++q)
+            if (q != e->peers.rank && e->peers.win[q]) cudaIpcCloseMemHandle(e->peers.win[q]);
+    cudaFree(e->d_xchg);
     for (auto &ev : e->ev_scan) if (ev) cudaEventDestroy(ev);
     if (e->chunk_ready) cudaEventDestroy(e->chunk_ready);
     if (e->ev_begin) cudaEventDestroy(e->ev_begin);
@@ -375,6 +385,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     if (n == "mode") e->mode = (int)v;
     else if (n == "presample_stride") e->presample_stride = std::max(1, (int)v);
     else if (n == "window_sigmas") e->window_sigmas = (float)v;
+    else if (n == "predict_bias") e->predict_bias = (float)v;
     else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(kTileBytes - 1));
     else if (n == "staging_threads") e->staging_threads = std::max(-1, (int)v);
     else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
@@ -868,7 +879,7 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if (mode == PAPR_MODE_FUSED) {
         papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES), stride,
                               e->grid, e->d_pre_cta, e->stream);
-        papr_launch_plan_pred(nullptr, e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas,
+        papr_launch_plan_pred(nullptr, e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas, e->predict_bias,
                               1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
         papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
         e->launches += 3;
@@ -952,7 +963,7 @@ extern "C" int papr_fused_scan(papr_engine *e, const float *d_iq, uint64_t n, ui
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
     CU(cudaMemcpyAsync(e->d_pre4, pre, sizeof(double) * 4, cudaMemcpyHostToDevice, e->stream));
-    papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas,
+    papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas, e->predict_bias,
                           1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
     papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 2;
@@ -1031,7 +1042,7 @@ extern "C" int papr_shard_scan_async(papr_engine *e, const float *d_iq, uint64_t
     }
     if ((rc = enqueue_reset(e))) return rc;
     if (fused) {
-        papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas,
+        papr_launch_plan_pred(e->d_pre4, nullptr, 0, e->tables(graph), e->window_sigmas, e->predict_bias,
                               1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
         papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
         e->launches += 2;
@@ -1076,6 +1087,108 @@ extern "C" int papr_shard_finish(papr_engine *e, int graph, papr_result *out)
     out->mode_used = e->shard_mode;
     out->fused_miss = redo;
     return redo; // 1: run papr_shard_counts_async(..., fused = 0, ...) on every rank, reduce, finish again
+}
+
+// ------------------------------------------------------------------------------------------------
+// sharded analysis with the exchanges fused into the kernels over peer memory (NVLink): one call per
+// rank, the same five-kernel chain as the single-GPU fused analysis plus one tiny summing kernel
+// ------------------------------------------------------------------------------------------------
+extern "C" int papr_xchg_export(papr_engine *e, void *handle64)
+{
+    if (!e || !handle64) return PAPR_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaSetDevice(e->device);
+    if (!e->d_xchg) {
+        CU(cudaMalloc(&e->d_xchg, sizeof(PaprXchg)));
+        CU(cudaMemset(e->d_xchg, 0, sizeof(PaprXchg)));
+        CU(cudaDeviceSynchronize()); // zeroed before any peer can learn the handle
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->d_xchg));
+    memcpy(handle64, &h, 64);
+    return PAPR_OK;
+}
+
+extern "C" int papr_xchg_attach(papr_engine *e, int rank, int world, const void *handles)
+{
+    if (!e || !handles || world < 1 || world > PAPR_XCHG_MAX_RANKS || rank < 0 || rank >= world) return PAPR_ERR_ARG;
+    if (!e->d_xchg) return fail(e, PAPR_ERR_ARG, "papr_xchg_export must run first");
+    if (e->xchg_attached) return fail(e, PAPR_ERR_ARG, "already attached");
+    cudaSetDevice(e->device);
+    PaprPeers pp = {};
+    pp.rank = rank;
+    pp.world = world;
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) { pp.win[q] = e->d_xchg; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * q, 64);
+        void *ptr = nullptr;
+        cudaError_t er = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (er != cudaSuccess) {
+            for (int k = 0; k < q; ++k)
+                if (k != rank && pp.win[k]) cudaIpcCloseMemHandle(pp.win[k]);
+            cudaGetLastError();
+            return fail(e, PAPR_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(er));
+        }
+        pp.win[q] = (PaprXchg *)ptr;
+    }
+    e->peers = pp;
+    e->xchg_attached = true;
+    return PAPR_OK;
+}
+
+extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_t n, uint64_t first, int graph,
+                                      papr_result *out)
+{
+    if (!e || !out || (n && !d_iq)) return PAPR_ERR_ARG;
+    if (!e->xchg_attached) return fail(e, PAPR_ERR_ARG, "papr_xchg_attach must run first");
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    memset(out, 0, offsetof(papr_result, level));
+    out->mode_used = PAPR_MODE_FUSED;
+    e->shard_mode = PAPR_MODE_FUSED;
+    int rc;
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    if ((rc = enqueue_reset(e))) return rc;
+    papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
+                          presample_stride_for(e, n, graph), e->grid, e->d_pre_cta, e->stream);
+    papr_launch_plan_pred_x(e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas, e->predict_bias,
+                            1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->peers,
+                            ++e->xseq[XK_PRE], e->stream);
+    papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
+    e->launches += 3;
+    if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
+    papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
+                                  &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
+                                  ++e->xseq[XK_STATS], e->stream);
+    e->launches += 1;
+    if ((rc = enqueue_resolve(e))) return rc;
+    papr_launch_counts_x(e->d_out->counts, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
+    e->launches += 1;
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->h_out->o.plan.pad) return fail(e, PAPR_ERR_INTERNAL, "peer exchange timed out (a rank did not take part)");
+    stats_to_host(e->h_out->o.merged, &out->stats);
+    // merged stats and the summed status word are identical on every rank, so every rank takes the
+    // same branch here: thresholds outside the predicted windows somewhere -> exact pass everywhere
+    if (collect(e, graph, out, true)) {
+        out->fused_miss = 1;
+        if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
+        CU(cudaMemsetAsync(e->d_work, 0, offsetof(DevWork, wp), e->stream)); // histogram scratch only
+        if ((rc = enqueue_hist_exact(e, d_iq, n, true))) return rc;
+        papr_launch_counts_x(e->d_out->counts, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
+        e->launches += 1;
+        if ((rc = enqueue_fetch(e))) return rc;
+        CU(cudaEventRecord(e->ev_end, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->h_out->o.plan.pad) return fail(e, PAPR_ERR_INTERNAL, "peer exchange timed out (a rank did not take part)");
+        if (e->h_out->o.counts[PAPR_MAX_LEVELS] != 0) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+        for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)e->h_out->o.counts[j];
+    }
+    finish_timing(e, out);
+    return PAPR_OK;
 }
 
 extern "C" int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first, uint64_t n, uint64_t seed)

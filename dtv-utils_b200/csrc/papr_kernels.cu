@@ -21,6 +21,7 @@
 //     the threshold's cell + the fine counters above the threshold inside its cell.  Exact.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "papr_device.cuh"
@@ -374,14 +375,15 @@ __device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, Papr
 // which the reference's loops reach level j are tabulated once with the HOST libm, so only IEEE
 // double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
 __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
-                                 PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word)
+                                 PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
+                                 size_t stride_bytes = sizeof(PaprDevStats))
 {
     __shared__ int s_L;
     __shared__ double s_avg;
     if (threadIdx.x == 0) {
         PaprDevStats m = parts[0];
         for (int p = 1; p < nparts; ++p) {
-            const PaprDevStats q = parts[p];
+            const PaprDevStats q = *reinterpret_cast<const PaprDevStats *>(reinterpret_cast<const char *>(parts) + p * stride_bytes);
             m.sum += q.sum;
             m.n += q.n;
             for (int k = 0; k < PAPR_NTRACK; ++k)
@@ -591,24 +593,17 @@ __device__ int assign_slots(const unsigned char *s_flag, int ncells, int sh, int
 
 // Fused mode.  pre4 = {sum, sum of squares, count} of batch sums already reduced over ranks, or
 // (single shard) nctas > 0: fold this GPU's CTA triples here and skip the separate reduce launch.
-__global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, const double *cta_pre, int nctas,
-                                                              PaprTables tb, float sigmas, int fine_slots,
-                                                              PaprPlan *plan, unsigned *fine_base)
+__device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, float sigmas, float bias, int fine_slots,
+                               PaprPlan *plan, unsigned *fine_base, int xchg_timeout)
 {
     __shared__ unsigned char s_flag[PAPR_NCELLS_MAX];
     __shared__ int s_scan[1024];
     __shared__ int s_cov;
     const int t = threadIdx.x;
-    double pre[3];
-    if (nctas > 0) {
-        reduce_pre(cta_pre, nctas, pre);
-    } else {
-        pre[0] = pre4[0]; pre[1] = pre4[1]; pre[2] = pre4[2];
-    }
     const double s1 = pre[0], s2 = pre[1], cnt = pre[2];
     PaprPlan pl;
     pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
-    pl.levels_covered = 0; pl.window = 0.f; pl.pad = 0; pl.avg_pred = 0.0;
+    pl.levels_covered = 0; pl.window = 0.f; pl.pad = xchg_timeout; pl.avg_pred = 0.0;
     const bool ok = cnt >= 16.0 && s1 > 0.0 && isfinite(s1) && isfinite(s2);
     if (!ok) { // nothing to predict from: the exact pass will run
         for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) fine_base[c] = 0;
@@ -620,7 +615,7 @@ __global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4
     if (!(var_b > 0.0)) var_b = 0.0;
     const double se_rel = sqrt(var_b / cnt) / mean_b;
     const double w = (double)sigmas * se_rel + 0x1p-18; // floor: a few float32 ulps of the thresholds
-    const double avg = mean_b / (double)PAPR_BATCH_SAMPLES;
+    const double avg = mean_b / (double)PAPR_BATCH_SAMPLES * (double)bias; // bias: test hook (1.0), forces a miss
     const int sh = PAPR_SH_MIN;
     float lo0 = __double2float_rd(avg * (1.0 - w));
     if (!(lo0 > 0.f)) lo0 = 0.f;
@@ -654,10 +649,23 @@ __global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4
     }
 }
 
-void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas,
+__global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, const double *cta_pre, int nctas,
+                                                              PaprTables tb, float sigmas, float bias, int fine_slots,
+                                                              PaprPlan *plan, unsigned *fine_base)
+{
+    double pre[3];
+    if (nctas > 0) {
+        reduce_pre(cta_pre, nctas, pre);
+    } else {
+        pre[0] = pre4[0]; pre[1] = pre4[1]; pre[2] = pre4[2];
+    }
+    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, 0);
+}
+
+void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias,
                            int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
 {
-    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, cta_pre, nctas, t, sigmas, fine_slots, plan, fine_base);
+    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base);
 }
 
 // Exact thresholds known (two-pass mode, or redo after a fused miss): ambiguous = the cells that hold
@@ -769,6 +777,156 @@ void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const 
                          int grid, cudaStream_t s)
 {
     papr_count_kernel<<<grid, 256, 0, s>>>(plan, fine_base, lv, g_hist, g_fine, g_over, counts, status_word);
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory exchange (one process per GPU, windows mapped into every rank with cudaIpc): the three
+// latency-sized exchanges of a sharded analysis, done inside the kernels that produce and consume the
+// values instead of three collective launches in between.  papr_device.cuh: PaprXchg.
+// ------------------------------------------------------------------------------------------------
+#define XCHG_TIMEOUT_NS 4000000000ull // a peer that has not published after 4 s is not going to
+
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ u64 ld_volatile(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ u64 global_timer_ns()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All threads of ONE CTA: copy `words` u64 from src into the field at `field_off` of slot[rank] in
+// every rank's window (NVLink stores for the peers, a local store for the own window), then raise
+// flag[kind][rank] = seq everywhere with a system-scope release.
+__device__ void xchg_publish(const PaprPeers &pp, int kind, size_t field_off, const u64 *src, int words, u64 seq)
+{
+    for (int r = 0; r < pp.world; ++r) {
+        u64 *dst = reinterpret_cast<u64 *>(reinterpret_cast<char *>(&pp.win[r]->slot[pp.rank]) + field_off);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->flag[kind][pp.rank], seq);
+}
+
+// All threads of ONE CTA: wait until every rank's publication `seq` of `kind` has landed in the own
+// window.  Returns false if a peer did not show up in time (the caller reports it, nothing hangs).
+__device__ bool xchg_wait(const PaprPeers &pp, int kind, u64 seq)
+{
+    __shared__ int s_late;
+    if (threadIdx.x == 0) s_late = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world) {
+        const u64 *f = &pp.win[pp.rank]->flag[kind][threadIdx.x];
+        const u64 t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < seq) {
+            if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) { atomicExch(&s_late, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    return s_late == 0;
+}
+
+// fused mode, sharded: fold this GPU's presample triples, publish them, wait for the other ranks',
+// add them up in rank order (identical on every rank) and plan from the global prediction
+__global__ void __launch_bounds__(1024) papr_plan_pred_x_kernel(const double *cta_pre, int nctas, PaprTables tb,
+                                                                float sigmas, float bias, int fine_slots, PaprPlan *plan,
+                                                                unsigned *fine_base, PaprPeers pp, u64 seq)
+{
+    __shared__ u64 s_mine[4];
+    double pre[3];
+    reduce_pre(cta_pre, nctas, pre);
+    if (threadIdx.x == 0) {
+        s_mine[0] = (u64)__double_as_longlong(pre[0]);
+        s_mine[1] = (u64)__double_as_longlong(pre[1]);
+        s_mine[2] = (u64)__double_as_longlong(pre[2]);
+        s_mine[3] = 0;
+    }
+    __syncthreads();
+    xchg_publish(pp, XK_PRE, offsetof(PaprXchgSlot, pre), s_mine, 4, seq);
+    const bool ok = xchg_wait(pp, XK_PRE, seq);
+    pre[0] = pre[1] = pre[2] = 0.0;
+    for (int q = 0; q < pp.world; ++q) {
+        const u64 *src = reinterpret_cast<const u64 *>(pp.win[pp.rank]->slot[q].pre);
+        pre[0] += __longlong_as_double((long long)ld_volatile(src));
+        pre[1] += __longlong_as_double((long long)ld_volatile(src + 1));
+        pre[2] += __longlong_as_double((long long)ld_volatile(src + 2));
+    }
+    if (!ok) pre[2] = 0.0; // no plan: the result is reported as failed anyway
+    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, ok ? 0 : 1);
+}
+
+void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
+                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, u64 seq, cudaStream_t s)
+{
+    papr_plan_pred_x_kernel<<<1, 1024, 0, s>>>(cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base, pp, seq);
+}
+
+// sharded: CTA partials -> this shard's pass-1 state -> published; every rank's state collected and
+// merged in rank order (first occurrence preserved); avg, L and the level table of the WHOLE capture
+__global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
+                                                                      PaprDevStats *local, PaprTables tb, int graph,
+                                                                      PaprDevStats *merged, PaprDevLevels *lv,
+                                                                      u64 *status_word, PaprPlan *plan, PaprPeers pp,
+                                                                      u64 seq)
+{
+    reduce_partials(wp, nctas, n, local);
+    __threadfence();
+    __syncthreads(); // thread 0's *local is visible to the CTA
+    xchg_publish(pp, XK_STATS, offsetof(PaprXchgSlot, stats), reinterpret_cast<const u64 *>(local),
+                 (int)(sizeof(PaprDevStats) / 8), seq);
+    const bool ok = xchg_wait(pp, XK_STATS, seq);
+    if (!ok && threadIdx.x == 0) plan->pad = 1;
+    __shared__ PaprDevStats s_parts[PAPR_XCHG_MAX_RANKS];
+    for (int i = threadIdx.x; i < pp.world * (int)(sizeof(PaprDevStats) / 8); i += blockDim.x) {
+        const int q = i / (int)(sizeof(PaprDevStats) / 8), w = i % (int)(sizeof(PaprDevStats) / 8);
+        reinterpret_cast<u64 *>(&s_parts[q])[w] = ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats) + w);
+    }
+    __syncthreads();
+    merge_and_levels(s_parts, pp.world, tb, graph, merged, lv, status_word);
+}
+
+void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
+                                   PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
+                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)
+{
+    papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq);
+}
+
+// sharded: publish this shard's level counts (+ status word), collect every rank's, add them up
+__global__ void __launch_bounds__(1024) papr_counts_x_kernel(u64 *counts, PaprPlan *plan, PaprPeers pp, u64 seq)
+{
+    xchg_publish(pp, XK_COUNTS, offsetof(PaprXchgSlot, counts), counts, PAPR_MAX_LEVELS + 1, seq);
+    const bool ok = xchg_wait(pp, XK_COUNTS, seq);
+    if (!ok && threadIdx.x == 0) plan->pad = 1;
+    for (int i = threadIdx.x; i <= PAPR_MAX_LEVELS; i += blockDim.x) {
+        u64 acc = 0;
+        for (int q = 0; q < pp.world; ++q) acc += ld_volatile(&pp.win[pp.rank]->slot[q].counts[i]);
+        counts[i] = acc;
+    }
+}
+
+void papr_launch_counts_x(u64 *counts, PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)
+{
+    papr_counts_x_kernel<<<1, 1024, 0, s>>>(counts, plan, pp, seq);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -61,7 +61,8 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_engine_device_buffer", "papr_shard_presample_async", "papr_shard_scan_async",
                "papr_shard_counts_async", "papr_shard_finish", "papr_multi_create", "papr_multi_destroy",
                "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
-               "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain"]
+               "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain",
+               "papr_xchg_export", "papr_xchg_attach", "papr_shard_analyze_p2p"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -120,6 +121,9 @@ def load_library(path: Optional[str] = None):
     lib.papr_seqsum_prepare.argtypes = [vp, vp, u64, C.POINTER(C.c_double)]
     lib.papr_seqsum_runs.argtypes = [vp, vp, u64, C.c_double]
     lib.papr_seqsum_chain.argtypes = [vp, vp, u64, C.POINTER(C.c_double)]
+    lib.papr_xchg_export.argtypes = [vp, C.c_char_p]
+    lib.papr_xchg_attach.argtypes = [vp, i32, i32, C.c_char_p]
+    lib.papr_shard_analyze_p2p.argtypes = [vp, vp, u64, u64, i32, C.POINTER(PaprResult)]
     if path is None:
         _lib = lib
     return lib
@@ -299,6 +303,21 @@ class Engine:
         s = C.c_double(state)
         self._check(self.lib.papr_seqsum_chain(self.h, _ptr(d_iq), nsamples, C.byref(s)), "papr_seqsum_chain")
         return s.value
+
+    # exchanges fused into the kernels over peer memory (see include/papr_b200.h) -------------------
+    def xchg_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.papr_xchg_export(self.h, buf), "papr_xchg_export")
+        return buf.raw
+
+    def xchg_attach(self, rank: int, world: int, handles: bytes):
+        self._check(self.lib.papr_xchg_attach(self.h, rank, world, handles), "papr_xchg_attach")
+
+    def shard_analyze_p2p(self, d_iq, nsamples: int, first_index: int, graph: bool) -> PaprResult:
+        res = PaprResult()
+        self._check(self.lib.papr_shard_analyze_p2p(self.h, _ptr(d_iq), nsamples, first_index, int(bool(graph)),
+                                                    C.byref(res)), "papr_shard_analyze_p2p")
+        return res
 
     # stream-ordered stages (see include/papr_b200.h) ---------------------------------------------------
     def device_buffer(self, which: int, dtype):
@@ -504,14 +523,50 @@ def _chain_sequential_sum(engine, d_iq, nsamples, rank, world, dev, group, fallb
     return state
 
 
+def attach_peer_exchange(engine: "Engine", group=None) -> bool:
+    """Map every rank's exchange window into every other rank (cudaIpc over NVLink) so that
+    papr_shard_analyze_p2p can run.  Collective: every rank of `group` must call it.  Returns False
+    (on every rank) when any rank could not attach, e.g. no peer access; the NCCL path remains."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ok = world <= 16 and os.environ.get("PAPR_B200_EXCHANGE", "").lower() != "nccl"
+    handle = b""
+    if ok:
+        try:
+            handle = engine.xchg_export()
+        except PaprError:
+            ok = False
+    gathered = [None] * world
+    dist.all_gather_object(gathered, handle if ok else b"", group=group)
+    ok = ok and all(len(h) == 64 for h in gathered)
+    if ok:
+        try:
+            engine.xchg_attach(rank, world, b"".join(gathered))
+        except PaprError:
+            ok = False
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group):
-    """NCCL path: kernels and the three tiny collectives are enqueued back to back on the engine's
-    stream, operating in place on the engine's device buffers; one host synchronisation at the end."""
+    """Device-resident shards, one process per GPU.  Fused mode: ONE library call per rank, the three
+    exchanges happen inside the kernels over peer memory (papr_shard_analyze_p2p).  Otherwise (two-pass
+    mode, or peer mapping unavailable) the NCCL path: kernels and three tiny collectives enqueued back
+    to back on the engine's stream, in place on the engine's device buffers; one host synchronisation."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     fused = mode != MODE_TWO_PASS
+    if fused:
+        p2p = getattr(engine, "_p2p", None)
+        if p2p is None:
+            p2p = engine._p2p = attach_peer_exchange(engine, group)
+        if p2p:
+            return engine.shard_analyze_p2p(d_iq, nsamples, first_index, graph)
     st = getattr(engine, "_xchg", None)
     if st is None:
         st = engine._xchg = {

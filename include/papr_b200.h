@@ -91,7 +91,8 @@ const char *papr_last_error(const papr_engine *e); /* e may be NULL: last create
 /* cudaStream_t the engine launches on (for callers that time or order against it). */
 void *papr_engine_stream(papr_engine *e);
 /* Tunables by name ("mode", "presample_stride", "window_sigmas", "chunk_bytes", "staging_threads",
- * "fused_min_samples", "fine_bytes_log2", "max_resident_bytes": host-side captures larger than this
+ * "fused_min_samples", "fine_bytes_log2", "predict_bias" (test hook: scales the fused mode's predicted
+ * mean; anything but 1.0 provokes the a-posteriori miss and the exact redo), "max_resident_bytes": host-side captures larger than this
  * (default 0 = what the GPU has free, less 1 GiB) are not kept resident in HBM but streamed twice,
  * like the reference reads its file twice (papr.c:142); "exact_sum": -1 (default) = emulate the reference's sequential
  * double sum (papr.c:104) bit for bit on the file/host path only, 0 = never, 1 = also on the
@@ -179,6 +180,21 @@ int papr_shard_scan_async(papr_engine *e, const float *d_iq, uint64_t nsamples, 
 int papr_shard_counts_async(papr_engine *e, const void *d_all_stats, int nparts, int graph, int fused,
                             const float *d_iq, uint64_t nsamples);
 int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
+
+/* The same sharded analysis with the three exchanges fused INTO the kernels over peer memory (NVLink,
+ * one process per GPU): every engine owns a small window in device memory that the other ranks map
+ * with cudaIpc; the producing kernel stores its values into every peer's window and raises a flag,
+ * the consuming kernel polls its own window - no collective launches in between.
+ *   export  -> 64-byte cudaIpcMemHandle_t of this engine's window; the caller gathers all ranks'
+ *   attach  -> maps the other ranks' windows (world <= 16; every rank must attach before any analyses)
+ *   papr_shard_analyze_p2p -> called by EVERY rank with its byte range; the whole-capture result on
+ *              every rank.  Fused mode; on a miss every rank re-runs the exact pass (same decision
+ *              everywhere, because the merged statistics and the summed status word are identical).
+ * A rank that never calls leaves the others with PAPR_ERR_INTERNAL after a 4 s device-side timeout. */
+int papr_xchg_export(papr_engine *e, void *handle64);
+int papr_xchg_attach(papr_engine *e, int rank, int world, const void *handles /* world x 64 bytes */);
+int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index, int graph,
+                           papr_result *out);
 
 /* papr.c:104 for a capture sharded over ranks: the reference's SEQUENTIAL double sum, bit for bit
  * (DESIGN.md section 5).  On the resident shard [d_iq, d_iq + 2*nsamples) of every rank:

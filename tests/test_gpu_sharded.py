@@ -33,6 +33,25 @@ def test_stream_ordered_stages_world1(built):
                 for mode in (1, 2):
                     res = built.analyze_sharded(eng, d, n, 0, graph, mode=mode)
                     assert built.format_result(res) == want, (name, graph, mode)
+        # fused mode went through the peer-memory exchange kernels (world 1: the own window only) ...
+        assert eng._p2p is True
+        # ... and the NCCL path gives the same text
+        eng._p2p = False
+        f = np.frombuffer(fixtures.image("appA_1M"), np.float32)
+        d = torch.from_numpy(f.copy()).cuda()
+        for graph in (False, True):
+            res = built.analyze_sharded(eng, d, f.size // 2, 0, graph, mode=2)
+            assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), graph)
+        eng._p2p = True
+        # forced miss (predicted mean off by 5 %): the exact thresholds fall outside the windows -> status
+        # word != 0 after the in-kernel sum -> exact pass, still the right text
+        big = fixtures.siggen(0, 1 << 22, 9)
+        d = torch.from_numpy(big).cuda()
+        eng.set("predict_bias", 1.05)
+        res = built.analyze_sharded(eng, d, 1 << 22, 0, True, mode=2)
+        eng.set("predict_bias", 1.0)
+        assert res.fused_miss == 1
+        assert built.format_result(res) == oracle_binding.run_image(big.tobytes(), True)
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -59,6 +78,14 @@ for graph in (False, True):
     for mode in (1, 2):
         res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=mode)
         ok &= pb.format_result(res) == want
+    ok &= eng._p2p is True          # mode 2 ran with the exchanges inside the kernels over NVLink peer memory
+    eng._p2p = False                # the NCCL path: same text
+    ok &= pb.format_result(pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)) == want
+    eng._p2p = True
+    eng.set("predict_bias", 1.05)   # forced miss: every rank must take the exact-pass branch together
+    res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)
+    eng.set("predict_bias", 1.0)
+    ok &= res.fused_miss == 1 and pb.format_result(res) == want
     pinned = d.cpu().pin_memory()
     res = pb.analyze_sharded(eng, None, n, rank * n, graph, host_image=pinned)
     ok &= pb.format_result(res) == want

@@ -34,7 +34,7 @@ int main(int argc, char **argv)
         tb.nlevels_max = graph ? PAPR_MAX_LEVELS : 256;
         int stride = graph ? 32 : 128;
         papr_launch_presample(iq, n, stride, grid, prewp, 0);
-        papr_launch_plan_pred(nullptr, prewp, grid, tb, 5.0f, 2048, plan, fb, 0);
+        papr_launch_plan_pred(nullptr, prewp, grid, tb, 5.0f, 1.0f, 2048, plan, fb, 0);
         PaprPlan hp; CK(cudaMemcpy(&hp, plan, sizeof(hp), cudaMemcpyDeviceToHost));
         printf(" graph=%d plan: sh=%d base=%d ncells=%d n_amb=%d cov=%d w=%g\n", graph, hp.sh, hp.cell_base, hp.ncells, hp.n_amb, hp.levels_covered, hp.window);
         PaprScanArgs a; a.iq = iq; a.nsamples = n; a.first_index = 0; a.wp = wp; a.plan = plan; a.fine_base = fb; a.g_hist = hist; a.g_fine = fine; a.g_over = over;
