@@ -1095,7 +1095,11 @@ __device__ __forceinline__ SeqRun seq_compose(const SeqRun &a, const SeqRun &b)
 }
 
 // One sample's effect on the two candidate states (even / odd entry), papr.c:104 in integer form.
-__device__ __forceinline__ void seq_step(float v, int U, u64 &d0, u64 &d1)
+// The states m0 = d0 and m1 = 1 + d1 receive the same increment from every sample except a tie
+// (fraction exactly 1/2) met while they still differ by one: then the odd one rounds up, and they
+// either merge (gap 0) or end up two apart (gap 2) - and move in lockstep ever after.  So one running
+// increment d0 plus the gap (0, 1 or 2) describes both; d1 = d0 + gap - 1.
+__device__ __forceinline__ void seq_step(float v, int U, u64 &d0, unsigned &gap)
 {
     const unsigned b = __float_as_uint(v);
     if (b == 0) return;
@@ -1104,15 +1108,16 @@ __device__ __forceinline__ void seq_step(float v, int U, u64 &d0, u64 &d1)
     const int E = (int)(e ? e : 1u) - 150;
     const int shift = U - E;
     if (shift <= 0) {            // v is a whole number of ulps: exact add
-        const u64 q = (u64)M << (-shift);
-        d0 += q; d1 += q;
+        d0 += (u64)M << (-shift);
     } else if (shift <= 24) {    // q ulps plus a fraction f = rem / 2^shift
         const u64 q = M >> shift;
         const unsigned rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
-        u64 r0 = 0, r1 = 0;
-        if (rem > half) { r0 = 1; r1 = 1; }
-        else if (rem == half) { r0 = (d0 + q) & 1; r1 = (1 + d1 + q) & 1; } // tie: to even
-        d0 += q + r0; d1 += q + r1;
+        u64 r0 = rem > half ? 1u : 0u;
+        if (rem == half) {       // tie: to even
+            r0 = (d0 + q) & 1;
+            if (gap == 1) gap = r0 ? 0u : 2u;
+        }
+        d0 += q + r0;
     }                            // shift >= 25: f < 1/2 and q = 0, the add rounds back
 }
 
@@ -1135,7 +1140,8 @@ __global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64
         const int U = k - 52;             // exponent of the binade's ulp
         const u64 s0 = (u64)tile * PAPR_SEQ_TILE + (u64)t * SEQ_PER;
         const float4 *p = reinterpret_cast<const float4 *>(iq + 2 * s0);
-        u64 d0 = 0, d1 = 0;
+        u64 d0 = 0;
+        unsigned gap = 1;
         if (s0 + SEQ_PER <= nsamples) {
 #pragma unroll 1
             for (int j = 0; j < SEQ_PER / 2; j += 4) {
@@ -1144,18 +1150,18 @@ __global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64
                 for (int u = 0; u < 4; ++u) q[u] = __ldg(p + j + u);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    seq_step(power_of(q[u].x, q[u].y), U, d0, d1);
-                    seq_step(power_of(q[u].z, q[u].w), U, d0, d1);
+                    seq_step(power_of(q[u].x, q[u].y), U, d0, gap);
+                    seq_step(power_of(q[u].z, q[u].w), U, d0, gap);
                 }
             }
         } else { // ragged end of the capture
             for (u64 s = s0; s < nsamples && s < s0 + SEQ_PER; ++s) {
                 const float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s);
-                seq_step(power_of(h.x, h.y), U, d0, d1);
+                seq_step(power_of(h.x, h.y), U, d0, gap);
             }
         }
         SeqRun r;
-        r.d0 = d0; r.d1 = d1;
+        r.d0 = d0; r.d1 = d0 + gap - 1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { // ordered: lane l (multiple of 2o) <- l then l+o
             SeqRun nb;
