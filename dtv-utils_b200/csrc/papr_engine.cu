@@ -695,6 +695,8 @@ static int seq_tile_sums(papr_engine *e, const float *d_iq, u64 n)
 // Returns 1 if a tile sum is NaN/Inf (the reference's sum is too: nothing to emulate).
 static int seq_classify(const double *tile_sum, u64 ntiles, double *pre_io, short *code)
 {
+    // biased exponent field of a non-negative double; [2^k, 2^(k+1)) <=> field == k + 1023
+    auto expo = [](double x) { u64 b; memcpy(&b, &x, 8); return (int)(b >> 52); };
     double pre = *pre_io;
     for (u64 t = 0; t < ntiles; ++t) {
         const double ts = tile_sum[t];
@@ -703,11 +705,11 @@ static int seq_classify(const double *tile_sum, u64 ntiles, double *pre_io, shor
         if (ts == 0.0) {
             c = PAPR_SEQ_ZERO;
         } else {
+            // the exact running sum lies within 1e-9 (relative) of these approximate prefixes: the tile is
+            // clean if both ends are normal numbers of the same binade
             const double lo = pre * (1.0 - 1e-9), hi = (pre + ts) * (1.0 + 1e-9);
-            if (lo > 0.0) {
-                const int k = std::ilogb(lo);
-                if (hi < std::ldexp(1.0, k + 1)) c = (short)k;
-            }
+            const int klo = expo(lo), khi = expo(hi);
+            if (lo > 0.0 && klo != 0 && klo == khi) c = (short)(klo - 1023);
         }
         code[t] = c;
         pre += ts;
