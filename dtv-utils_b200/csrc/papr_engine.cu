@@ -1,6 +1,8 @@
 // papr_engine.cu — the C ABI (include/papr_b200.h): engine lifetime, the device-resident analysis,
-// the host-buffer analysis (pinned double-buffered H2D overlapped with the statistics pass) and the
-// per-stage entry points for sharded callers.
+// the host-side analysis (files, pinned and pageable buffers streamed in chunks with the statistics
+// pass and the sequential-sum emulation running under the H2D shadow; re-streaming for captures larger
+// than HBM), the per-stage entry points for sharded callers, the sharded analysis with its exchanges
+// fused into the kernels over peer memory, and the single-process multi-GPU driver.
 //
 // One analysis is a single stream-ordered chain of launches with ONE host synchronisation at the
 // end: the reference's scalar epilogue (papr.c:131-141 / 164-173) is evaluated on the device from
