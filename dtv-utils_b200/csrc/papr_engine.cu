@@ -1448,7 +1448,8 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
     CU(cudaStreamSynchronize(e->stream));
     e->d2h += ntiles * 16;
     double s = 0.0;
-    if ((rc = seq_chain(e, g.n, &s, tile_fetcher(e, src, g, resident)))) return rc;
+    rc = seq_chain(e, g.n, &s, tile_fetcher(e, src, g, resident));
+    if (rc) return rc;
     e->h_out->pre4[0] = s;
     CU(cudaMemcpyAsync(&e->d_out->local.sum, &e->h_out->pre4[0], sizeof(double), cudaMemcpyHostToDevice, e->stream));
     *exact_done = true;
@@ -1487,7 +1488,8 @@ static int fix_nan_sign_streamed(papr_engine *e, const HostSource &src, const St
     const u64 k = e->h_out->nan_idx;
     if (k == ~0ull) return PAPR_OK;
     float pair[2];
-    if ((rc = tile_fetcher(e, src, g, false)(k - g.first, 1, pair))) return rc;
+    rc = tile_fetcher(e, src, g, false)(k - g.first, 1, pair);
+    if (rc) return rc;
     const bool neg = std::isnan(pair[1]) ? std::signbit(pair[1]) : std::signbit(pair[0]);
     st->sum = std::copysign(std::fabs(st->sum), neg ? -1.0 : 1.0);
     return PAPR_OK;
