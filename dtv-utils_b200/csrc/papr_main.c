@@ -129,11 +129,13 @@ int papr_main(int argc, char **argv)
             free(r);
             return 1;
         }
-        if (getenv("PAPR_B200_STATS"))
-            fprintf(stderr, "papr_b200: create_ms=%.1f analyze_ms=%.1f device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n",
-                    t1 - t0, t2 - t1, r->device_ms, r->scan_ms, r->kernel_launches, (unsigned long long)r->h2d_bytes);
         print_result(r);
+        const double t3 = now_ms();
         papr_engine_destroy(e);
+        if (getenv("PAPR_B200_STATS"))
+            fprintf(stderr, "papr_b200: create_ms=%.1f analyze_ms=%.1f destroy_ms=%.1f device_ms=%.3f scan_ms=%.3f launches=%u h2d=%llu\n",
+                    t1 - t0, t2 - t1, now_ms() - t3, r->device_ms, r->scan_ms, r->kernel_launches,
+                    (unsigned long long)r->h2d_bytes);
     }
     free(r);
     return 0;
