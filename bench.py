@@ -351,6 +351,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(args, pinned, n_host, graph, eng, pb)
         print(json.dumps(line), flush=True)
     if dist is not None:
+        pb.detach_peer_exchange(eng)  # unmap the peers' windows on every rank, barrier, only then tear down
+        eng.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0

@@ -7,7 +7,7 @@ the repo root: the directory name carries the reference's hyphen).
 """
 from .build import build, lib_path, cli_path  # noqa: F401
 from .papr import (Engine, MultiEngine, PaprError, PaprResult, PaprStats, analyze_sharded, attach_peer_exchange,  # noqa: F401
-                   format_result, levels, load_library, main, merge_stats)
+                   detach_peer_exchange, format_result, levels, load_library, main, merge_stats)
 
 __all__ = ["build", "lib_path", "cli_path", "Engine", "MultiEngine", "PaprError", "PaprResult", "PaprStats",
-           "analyze_sharded", "attach_peer_exchange", "format_result", "levels", "load_library", "main", "merge_stats"]
+           "analyze_sharded", "attach_peer_exchange", "detach_peer_exchange", "format_result", "levels", "load_library", "main", "merge_stats"]

@@ -350,6 +350,8 @@ extern "C" int papr_engine_create(int device, papr_engine **out)
     return PAPR_OK;
 }
 
+extern "C" int papr_xchg_detach(papr_engine *e);
+
 extern "C" void papr_engine_destroy(papr_engine *e)
 {
     if (!e) return;
@@ -367,9 +369,7 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     for (auto &ev : e->ring_free) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->seq_ev) if (ev) cudaEventDestroy(ev);
     cudaFree(e->d_ring);
-    if (e->xchg_attached)
-        for (int q = 0; q < e->peers.world; ++q)
-            if (q != e->peers.rank && e->peers.win[q]) cudaIpcCloseMemHandle(e->peers.win[q]);
+    papr_xchg_detach(e);
     cudaFree(e->d_xchg);
     for (auto &ev : e->ev_scan) if (ev) cudaEventDestroy(ev);
     if (e->chunk_ready) cudaEventDestroy(e->chunk_ready);
@@ -1138,6 +1138,23 @@ extern "C" int papr_xchg_attach(papr_engine *e, int rank, int world, const void 
     }
     e->peers = pp;
     e->xchg_attached = true;
+    return PAPR_OK;
+}
+
+// Unmap the other ranks' windows (the own one stays).  Callers detach on every rank and synchronise
+// among themselves BEFORE any rank destroys its engine: freeing an exported window that a peer still
+// has open is undefined.
+extern "C" int papr_xchg_detach(papr_engine *e)
+{
+    if (!e) return PAPR_ERR_ARG;
+    if (!e->xchg_attached) return PAPR_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int q = 0; q < e->peers.world; ++q)
+        if (q != e->peers.rank && e->peers.win[q]) cudaIpcCloseMemHandle(e->peers.win[q]);
+    e->peers = PaprPeers{};
+    e->xchg_attached = false;
+    cudaGetLastError();
     return PAPR_OK;
 }
 

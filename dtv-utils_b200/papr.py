@@ -62,7 +62,7 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_shard_counts_async", "papr_shard_finish", "papr_multi_create", "papr_multi_destroy",
                "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
                "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain",
-               "papr_xchg_export", "papr_xchg_attach", "papr_shard_analyze_p2p"]
+               "papr_xchg_export", "papr_xchg_attach", "papr_xchg_detach", "papr_shard_analyze_p2p"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -123,6 +123,7 @@ def load_library(path: Optional[str] = None):
     lib.papr_seqsum_chain.argtypes = [vp, vp, u64, C.POINTER(C.c_double)]
     lib.papr_xchg_export.argtypes = [vp, C.c_char_p]
     lib.papr_xchg_attach.argtypes = [vp, i32, i32, C.c_char_p]
+    lib.papr_xchg_detach.argtypes = [vp]
     lib.papr_shard_analyze_p2p.argtypes = [vp, vp, u64, u64, i32, C.POINTER(PaprResult)]
     if path is None:
         _lib = lib
@@ -312,6 +313,9 @@ class Engine:
 
     def xchg_attach(self, rank: int, world: int, handles: bytes):
         self._check(self.lib.papr_xchg_attach(self.h, rank, world, handles), "papr_xchg_attach")
+
+    def xchg_detach(self):
+        self._check(self.lib.papr_xchg_detach(self.h), "papr_xchg_detach")
 
     def shard_analyze_p2p(self, d_iq, nsamples: int, first_index: int, graph: bool) -> PaprResult:
         res = PaprResult()
@@ -549,6 +553,19 @@ def attach_peer_exchange(engine: "Engine", group=None) -> bool:
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     return bool(flag.item())
+
+
+def detach_peer_exchange(engine: "Engine", group=None) -> None:
+    """Collective counterpart of attach_peer_exchange: every rank unmaps its peers' windows, then all
+    ranks meet at a barrier, so that no rank frees its window while another still has it mapped.  Call
+    it before the engines are closed / the process group is destroyed."""
+    import torch.distributed as dist
+
+    if getattr(engine, "_p2p", None):
+        engine.xchg_detach()
+    engine._p2p = None
+    if dist.is_initialized():
+        dist.barrier(group=group)
 
 
 def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group):

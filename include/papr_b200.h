@@ -193,6 +193,8 @@ int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
  * A rank that never calls leaves the others with PAPR_ERR_INTERNAL after a 4 s device-side timeout. */
 int papr_xchg_export(papr_engine *e, void *handle64);
 int papr_xchg_attach(papr_engine *e, int rank, int world, const void *handles /* world x 64 bytes */);
+/* unmaps the peers' windows; detach on every rank, synchronise, THEN destroy the engines */
+int papr_xchg_detach(papr_engine *e);
 int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_t nsamples, uint64_t first_index, int graph,
                            papr_result *out);
 

@@ -52,6 +52,8 @@ def test_stream_ordered_stages_world1(built):
         eng.set("predict_bias", 1.0)
         assert res.fused_miss == 1
         assert built.format_result(res) == oracle_binding.run_image(big.tobytes(), True)
+        built.detach_peer_exchange(eng)
+        assert eng._p2p is None
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -94,6 +96,7 @@ for graph in (False, True):
     res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2, exact_sum=True)  # and on request for resident ones
     ok &= pb.format_result(res) == want and struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
 print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
+pb.detach_peer_exchange(eng); eng.close()
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if ok else 1)
 '''
