@@ -550,9 +550,13 @@ def attach_peer_exchange(engine: "Engine", group=None) -> bool:
             engine.xchg_attach(rank, world, b"".join(gathered))
         except PaprError:
             ok = False
-    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    return bool(flag.item())
+    agreed = bool(flag.item())
+    if ok and not agreed:  # some other rank could not attach: nobody uses the windows
+        engine.xchg_detach()
+    return agreed
 
 
 def detach_peer_exchange(engine: "Engine", group=None) -> None:

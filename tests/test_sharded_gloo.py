@@ -106,3 +106,60 @@ def test_two_rank_sharding_matches_reference(name, graph, fused, exact, built):
     want = open(os.path.join(ROOT, "tests", "golden", name + (".g.out" if graph else ".out")), "rb").read()
     # only fixtures with an even float count are used here, so no stale-Q tail is involved
     assert outs[0] == want and outs[1] == want
+
+
+def _attach_worker(rank, world, port, fail_rank, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import dtv_utils_b200 as pb
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class Windows:
+        """stand-in for the engine's exchange-window calls (the real ones need a GPU)"""
+        attached = detached = False
+
+        def xchg_export(self):
+            if rank == fail_rank == 0:
+                raise pb.PaprError("no peer access")
+            return bytes([rank]) * 64
+
+        def xchg_attach(self, r, w, handles):
+            assert (r, w) == (rank, world) and len(handles) == 64 * world
+            assert all(handles[64 * k] == k for k in range(world))  # gathered in rank order
+            if rank == fail_rank == 1:
+                raise pb.PaprError("cudaIpcOpenMemHandle failed")
+            self.attached = True
+
+        def xchg_detach(self):
+            self.detached = True
+
+    eng = Windows()
+    ok = pb.attach_peer_exchange(eng)
+    q.put((rank, ok, eng.attached, eng.detached))
+    eng._p2p = ok
+    pb.detach_peer_exchange(eng)
+    assert eng._p2p is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 0, 1], ids=["all_attach", "export_fails_on_0", "attach_fails_on_1"])
+def test_peer_exchange_attach_is_all_or_nothing(fail_rank, built):
+    """attach_peer_exchange: handles gathered in rank order; if ANY rank cannot export or map, EVERY
+    rank reports False (and a rank that did attach lets go again), so all ranks pick the same path."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() + fail_rank) % 90
+    procs = [ctx.Process(target=_attach_worker, args=(r, 2, port, fail_rank, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = {r: (ok, att, det) for r, ok, att, det in (q.get(timeout=120) for _ in procs)}
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    if fail_rank < 0:
+        assert outs == {0: (True, True, False), 1: (True, True, False)}
+    else:
+        assert outs[0][0] is False and outs[1][0] is False
+        assert all(det or not att for _, att, det in outs.values())  # whoever attached has detached again
