@@ -134,3 +134,55 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h")) or f == "Makefile":
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("the oracle", ""), os.path.join(d, f)
+
+
+# ---- the tables that let the GPU evaluate the reference's epilogue (papr.c:131-141 / 164-173) ----------
+def _device_epilogue(tables, summ, n, peak, L_max):
+    """What papr_levels_kernel (csrc/papr_kernels.cu: merge_and_levels) computes, restated with numpy's
+    IEEE double divide / multiply / compare and one rounding to float32 — no libm."""
+    pow10, ratio_min = tables
+    avg = np.float64(summ) / np.float64(n)
+    ratio = np.float64(np.float32(peak)) / avg
+    L = int(np.searchsorted(ratio_min[:L_max], ratio, side="right"))  # number of j with ratio >= ratio_min[j]
+    with np.errstate(over="ignore"):
+        level = (pow10[:L] * avg).astype(np.float32)
+    return L, level
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["1dB", "graph"])
+def test_device_epilogue_tables_agree_with_host_libm(built, graph):
+    """papr_host_build_tables (host libm, built once per engine) + plain IEEE arithmetic must give the
+    same number of levels and bit-identical thresholds as papr_levels (the reference's conversion
+    sequence with log10 / pow) — for thousands of random statistics, with peak/avg ratios placed on
+    and next to the dB boundaries where (int)papr steps."""
+    lib = built.load_library()
+    nmax = 2048 if graph else 256
+    pow10 = np.full(2048, np.inf)
+    ratio_min = np.full(2048, np.inf)
+    lib.papr_host_build_tables.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.papr_host_build_tables.restype = None
+    lib.papr_host_build_tables(int(graph), nmax, pow10.ctypes.data, ratio_min.ctypes.data)
+    assert np.all(np.diff(ratio_min[:nmax]) >= 0) and ratio_min[0] > 0
+    rng = np.random.default_rng(7)
+    cases = []
+    for _ in range(3000):
+        n = int(rng.integers(1, 1 << 40))
+        avg = float(np.exp(rng.uniform(-40, 20)))
+        papr_db = float(rng.uniform(0, min(60.0, 10 * np.log10(n))))  # peak <= sum: the peak is one of the samples
+        if rng.random() < 0.5:  # sit on a boundary of the level count (1 dB or 0.1 dB steps) and step around it
+            papr_db = round(papr_db, 0 if not graph else 1)
+        peak = np.float32(avg * 10 ** (papr_db / 10))
+        for nudge in (0, 1, -1):
+            pk = np.nextafter(peak, np.float32(np.inf if nudge > 0 else -np.inf)) if nudge else peak
+            cases.append((avg * n, n, float(pk)))
+    cases += [(1.0, 1, 1.0), (4.0, 4, 1.0), (4.0, 4, 4.0), (2.0 ** 60, 2 ** 62, 2.0 ** 60), (1e-40, 1000, 1e-42)]
+    st = built.PaprStats()
+    lv = (C.c_float * 2048)()
+    avg_c, papr_c = C.c_double(), C.c_float()
+    for summ, n, peak in cases:
+        st.n, st.sum, st.peak = n, summ, peak
+        L_host = lib.papr_levels(C.byref(st), int(graph), C.byref(avg_c), C.byref(papr_c), lv, 2048)
+        L_dev, level_dev = _device_epilogue((pow10, ratio_min), st.sum, n, st.peak, nmax)
+        assert L_dev == L_host, (summ, n, peak, papr_c.value)
+        host = np.frombuffer(lv, np.float32, L_host)
+        assert host.tobytes() == level_dev.tobytes(), (summ, n, peak)
