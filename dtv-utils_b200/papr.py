@@ -554,7 +554,18 @@ def attach_peer_exchange(engine: "Engine", group=None) -> bool:
     flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
     agreed = bool(flag.item())
-    if ok and not agreed:  # some other rank could not attach: nobody uses the windows
+    if agreed and dev == "cuda":
+        # prove the windows before relying on them: one tiny collective analysis through the in-kernel
+        # exchange (a peer whose stores do not arrive costs a 4 s device-side timeout here, once,
+        # instead of an error in the middle of the caller's work)
+        probe = torch.zeros(2 * 4096, dtype=torch.float32, device="cuda")
+        try:
+            engine.shard_analyze_p2p(probe, 4096, rank * 4096, False)
+        except PaprError:
+            flag.zero_()
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        agreed = bool(flag.item())
+    if ok and not agreed:  # some rank could not attach or the probe failed: nobody uses the windows
         engine.xchg_detach()
     return agreed
 
