@@ -102,17 +102,23 @@ enum { XK_PRE = 0, XK_STATS = 1, XK_COUNTS = 2 };
 struct PaprXchgSlot {
     double pre[4];                                   // presample {sum, sum of squares, count, -}
     PaprDevStats stats;                              // pass-1 state of the shard
-    unsigned long long counts[PAPR_MAX_LEVELS + 1];  // level counts + status word
+    // level counts + status word; two buffers used alternately (publication seq & 1): an analysis that
+    // publishes counts twice (fused miss -> exact redo) never overwrites what a peer may still be summing
+    unsigned long long counts[2][PAPR_MAX_LEVELS + 1];
 };
 
 struct PaprXchg {
     unsigned long long flag[3][PAPR_XCHG_MAX_RANKS];
+    // abort[q] != 0: rank q gave up waiting (timeout) during the exchange with that sequence number of
+    // kind XK_PRE; every later wait on any rank fails too, so all ranks report the same outcome
+    unsigned long long abort[PAPR_XCHG_MAX_RANKS];
     PaprXchgSlot slot[PAPR_XCHG_MAX_RANKS];
 };
 
 struct PaprPeers {
     PaprXchg *win[PAPR_XCHG_MAX_RANKS]; // win[rank] = the local window, the others are peer mappings
     int rank, world;
+    unsigned long long timeout_ns;      // how long a kernel waits for a peer's publication
 };
 
 // launchers (papr_kernels.cu)
@@ -153,7 +159,7 @@ void papr_launch_find_nan(const float *iq, unsigned long long nsamples, unsigned
                           unsigned long long *out_idx, int grid, cudaStream_t s);
 void papr_launch_tilesum(const float *iq, unsigned long long nsamples, double *tile_sum, int grid, cudaStream_t s);
 void papr_launch_seqsum(const float *iq, unsigned long long nsamples, const short *tile_code,
-                        void *tile_run /* {u64 d0, d1}[ntiles] */, int grid, cudaStream_t s);
+                        void *tile_run /* {double e0, e1}[ntiles] */, int grid, cudaStream_t s);
 int papr_seqsum_configure(void);
 void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
                              PaprPlan *plan, unsigned *fine_base, PaprPeers pp, unsigned long long seq, cudaStream_t s);
@@ -161,7 +167,7 @@ void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
                                    unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,
                                    unsigned long long seq, cudaStream_t s);
-void papr_launch_counts_x(unsigned long long *counts, PaprPlan *plan, PaprPeers pp, unsigned long long seq,
-                          cudaStream_t s);
+void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
+                          unsigned long long seq, cudaStream_t s);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

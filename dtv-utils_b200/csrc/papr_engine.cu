@@ -214,7 +214,7 @@ struct papr_engine {
     u64 seq_tiles = 0;
     double *d_tile_sum = nullptr, *h_tile_sum = nullptr;
     short *d_tile_code = nullptr, *h_tile_code = nullptr;
-    u64 *d_tile_run = nullptr, *h_tile_run = nullptr;
+    double *d_tile_run = nullptr, *h_tile_run = nullptr; // {increment for an even, an odd entry state} per tile
     float *h_tile_data = nullptr;
     unsigned seq_dirty = 0;
     const float *seq_sums_ptr = nullptr; // h_tile_sum currently holds the tile sums of this resident shard ...
@@ -249,6 +249,7 @@ struct papr_engine {
     PaprPeers peers = {};
     bool xchg_attached = false;
     u64 xseq[3] = {0, 0, 0};
+    double xchg_timeout_s = 30.0; // how long a kernel waits for a peer's publication before every rank gives up
     // timing / accounting
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_scan[4] = {nullptr, nullptr, nullptr, nullptr};
     int scan_pairs = 0;
@@ -279,6 +280,14 @@ static int fail(papr_engine *e, int code, const std::string &msg)
 {
     e->err = msg;
     return code;
+}
+
+// everything except the two big arrays (which are valid up to nlevels only): the statistics head AND the
+// diagnostics tail, so that a caller's stack struct never leaks garbage into fused_miss / the counters
+static void reset_result(papr_result *out)
+{
+    memset(out, 0, offsetof(papr_result, level));
+    memset(&out->mode_used, 0, sizeof(papr_result) - offsetof(papr_result, mode_used));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -393,7 +402,12 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
     else if (n == "exact_sum") e->exact_sum = (int)v;
-    else if (n == "fine_bytes_log2") e->fine_bytes_log2 = std::min(26, std::max(4, (int)v)); // <= the allocation
+    else if (n == "fine_bytes_log2") // <= the allocation, >= two slots of the finest cell size (u64 per float32 value)
+        e->fine_bytes_log2 = std::min(26, std::max(3 + PAPR_SH_MIN + 1, (int)v));
+    else if (n == "xchg_timeout_s") {
+        e->xchg_timeout_s = std::min(3600.0, std::max(0.001, v));
+        e->peers.timeout_ns = (u64)(e->xchg_timeout_s * 1e9);
+    }
     else if (n == "grid_per_sm") return fail(e, PAPR_ERR_ARG, "grid_per_sm is fixed at engine creation");
     else return fail(e, PAPR_ERR_ARG, "unknown tunable: " + n);
     return PAPR_OK;
@@ -669,10 +683,10 @@ static int ensure_seq_buffers(papr_engine *e, u64 ntiles)
     u64 cap = std::max<u64>(ntiles, 4096);
     CU(cudaMalloc(&e->d_tile_sum, cap * sizeof(double)));
     CU(cudaMalloc(&e->d_tile_code, cap * sizeof(short)));
-    CU(cudaMalloc(&e->d_tile_run, cap * 2 * sizeof(u64)));
+    CU(cudaMalloc(&e->d_tile_run, cap * 2 * sizeof(double)));
     CU(cudaHostAlloc(&e->h_tile_sum, cap * sizeof(double), cudaHostAllocDefault));
     CU(cudaHostAlloc(&e->h_tile_code, cap * sizeof(short), cudaHostAllocDefault));
-    CU(cudaHostAlloc(&e->h_tile_run, cap * 2 * sizeof(u64), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&e->h_tile_run, cap * 2 * sizeof(double), cudaHostAllocDefault));
     if (!e->h_tile_data) CU(cudaHostAlloc(&e->h_tile_data, (size_t)PAPR_SEQ_TILE * 8, cudaHostAllocDefault));
     e->seq_tiles = cap;
     return PAPR_OK;
@@ -727,7 +741,7 @@ static int seq_tile_runs(papr_engine *e, const float *d_iq, u64 n)
     if (ntiles == 0) return PAPR_OK;
     CU(cudaMemcpyAsync(e->d_tile_code, e->h_tile_code, ntiles * sizeof(short), cudaMemcpyHostToDevice, e->stream));
     papr_launch_seqsum(d_iq, n, e->d_tile_code, e->d_tile_run, (int)std::min<u64>((u64)e->num_sms * 8, ntiles), e->stream);
-    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->launches += 1;
     e->d2h += ntiles * 24;
@@ -743,7 +757,6 @@ typedef std::function<int(u64 first, u64 cnt, float *dst)> TileFetch;
 static int seq_chain(papr_engine *e, u64 n, double *s_io, const TileFetch &fetch)
 {
     const u64 ntiles = (n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
-    const u64 mant = (1ull << 52) - 1;
     double s = *s_io;
     for (u64 t = 0; t < ntiles; ++t) {
         const short code = e->h_tile_code[t];
@@ -753,11 +766,16 @@ static int seq_chain(papr_engine *e, u64 n, double *s_io, const TileFetch &fetch
             memcpy(&bits, &s, 8);
             const unsigned ef = (unsigned)(bits >> 52); // sign + exponent field; s in [2^k, 2^(k+1)) <=> ef == k + 1023
             if (ef != 0 && ef == (unsigned)((int)code + 1023)) {
-                const u64 m = (bits & mant) | (1ull << 52); // s = m * 2^(k-52), exactly
-                const u64 m2 = m + ((m & 1) ? e->h_tile_run[2 * t + 1] : e->h_tile_run[2 * t]);
-                if (m2 < (1ull << 53)) { // still inside the binade: the tile's run applies as computed
-                    bits = ((u64)ef << 52) | (m2 & mant);
-                    memcpy(&s, &bits, 8);
+                // s = m * ulp with m's parity in bit 0; the tile's increment for that parity is a whole number
+                // of ulps, so the add is exact as long as the result stays inside the binade - and a result
+                // that leaves it (or a run whose accumulators left it: increment >= 2^k) is never below top
+                const double inc = e->h_tile_run[2 * t + (bits & 1)];
+                const u64 top_bits = (u64)(ef + 1) << 52;
+                double top;
+                memcpy(&top, &top_bits, 8);
+                const double s2 = s + inc;
+                if (inc >= 0.0 && s2 < top) {
+                    s = s2;
                     continue;
                 }
             }
@@ -870,7 +888,7 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
     graph = graph ? 1 : 0;
     begin_analysis(e);
-    memset(out, 0, offsetof(papr_result, level));
+    reset_result(out);
     int mode = e->mode;
     const int stride = presample_stride_for(e, n, graph);
     if (mode == PAPR_MODE_AUTO) // fused pays off once the subsample is a small fraction of the shard
@@ -946,6 +964,7 @@ extern "C" int papr_ccdf_device(papr_engine *e, const float *d_iq, uint64_t n, c
 extern "C" int papr_fused_presample(papr_engine *e, const float *d_iq, uint64_t n, int graph, double pre[4])
 {
     if (!e || !pre || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
     begin_analysis(e);
     papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
                           presample_stride_for(e, n, graph ? 1 : 0), e->grid, e->d_pre_cta, e->stream);
@@ -1023,6 +1042,7 @@ extern "C" int papr_engine_device_buffer(papr_engine *e, int which, void **ptr, 
 extern "C" int papr_shard_presample_async(papr_engine *e, const float *d_iq, uint64_t n, int graph)
 {
     if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
+    if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
     begin_analysis(e);
     CU(cudaEventRecord(e->ev_begin, e->stream));
     papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
@@ -1081,7 +1101,7 @@ extern "C" int papr_shard_finish(papr_engine *e, int graph, papr_result *out)
     if (!e || !out) return PAPR_ERR_ARG;
     graph = graph ? 1 : 0;
     int rc;
-    memset(out, 0, offsetof(papr_result, level));
+    reset_result(out);
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1136,6 +1156,9 @@ extern "C" int papr_xchg_attach(papr_engine *e, int rank, int world, const void 
         }
         pp.win[q] = (PaprXchg *)ptr;
     }
+    pp.timeout_ns = (u64)(e->xchg_timeout_s * 1e9);
+    CU(cudaMemset(e->d_xchg->abort, 0, sizeof(e->d_xchg->abort))); // a fresh attachment starts unpoisoned
+    CU(cudaDeviceSynchronize());
     e->peers = pp;
     e->xchg_attached = true;
     return PAPR_OK;
@@ -1166,7 +1189,7 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     if ((uintptr_t)d_iq & 15) return fail(e, PAPR_ERR_ARG, "device pointer must be 16-byte aligned");
     graph = graph ? 1 : 0;
     begin_analysis(e);
-    memset(out, 0, offsetof(papr_result, level));
+    reset_result(out);
     out->mode_used = PAPR_MODE_FUSED;
     e->shard_mode = PAPR_MODE_FUSED;
     int rc;
@@ -1185,7 +1208,7 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
                                   ++e->xseq[XK_STATS], e->stream);
     e->launches += 1;
     if ((rc = enqueue_resolve(e))) return rc;
-    papr_launch_counts_x(e->d_out->counts, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
+    papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
     e->launches += 1;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
@@ -1199,7 +1222,7 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
         if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
         CU(cudaMemsetAsync(e->d_work, 0, offsetof(DevWork, wp), e->stream)); // histogram scratch only
         if ((rc = enqueue_hist_exact(e, d_iq, n, true))) return rc;
-        papr_launch_counts_x(e->d_out->counts, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
+        papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
         e->launches += 1;
         if ((rc = enqueue_fetch(e))) return rc;
         CU(cudaEventRecord(e->ev_end, e->stream));
@@ -1461,7 +1484,7 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
     CU(cudaGetLastError());
     if (!seq_ok || ntiles == 0) return PAPR_OK;
     // the runs come back, the host chains them in file order, the exact sum replaces the tree sum
-    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(e->h_tile_run, e->d_tile_run, ntiles * 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->d2h += ntiles * 16;
     double s = 0.0;
@@ -1534,7 +1557,7 @@ static int analyze_source(papr_engine *e, const HostSource &src, int graph, papr
 {
     graph = graph ? 1 : 0;
     begin_analysis(e);
-    memset(out, 0, offsetof(papr_result, level));
+    reset_result(out);
     out->mode_used = PAPR_MODE_TWO_PASS;
     int rc;
     StreamGeom g;
@@ -1874,7 +1897,7 @@ static int multi_analyze_source(papr_multi *m, const HostSource &whole, int grap
     per = std::max<u64>(chunk_samples, (per + chunk_samples - 1) / chunk_samples * chunk_samples);
     const int tail_rank = (int)std::min<u64>((u64)N - 1, npairs / per);
 
-    memset(out, 0, offsetof(papr_result, level));
+    reset_result(out);
     out->mode_used = PAPR_MODE_TWO_PASS;
     std::vector<papr_stats> st(N);
     std::vector<u64> ns(N, 0);

@@ -7,7 +7,7 @@
 //           papr.c:175-185   same with 0.1 dB levels (-g)
 //
 // How it is done here (HBM-bound byte/float work, no tensor cores):
-//   * one persistent grid (2 CTAs x 512 threads per SM); a warp owns 2 KiB-contiguous "batches"
+//   * one persistent grid (1 CTA x 1024 threads per SM); a warp owns 2 KiB-contiguous "batches"
 //     (32 lanes x 4 x 16-byte streaming loads in flight per lane), batches ascend per warp so a
 //     strict compare keeps the first occurrence;
 //   * extremes: per-lane FMNMX into batch maxima, one REDUX.MAX per tracker per batch, and only on the
@@ -103,7 +103,12 @@ template <bool STATS, bool HIST>
 __device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, unsigned bits)
 {
     // shared-window byte address of the sample's slot
-    const int d = max(min((int)(bits >> st.sh) - st.cell_base, st.ncells), -1);
+    int d = (int)(bits >> st.sh) - st.cell_base;
+    // a NaN power exceeds no level (`value > level[j]` is false, papr.c:148); only the stand-alone CCDF
+    // pass can meet one with levels to count against - with the statistics in the same sweep the sum is
+    // NaN too and the reference prints no levels at all
+    if (!STATS) d = bits > 0x7f800000u ? -1 : d;
+    d = max(min(d, st.ncells), -1);
     return st.smem_slot1 + ((unsigned)d << 2);
 }
 
@@ -784,7 +789,6 @@ void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const 
 // latency-sized exchanges of a sharded analysis, done inside the kernels that produce and consume the
 // values instead of three collective launches in between.  papr_device.cuh: PaprXchg.
 // ------------------------------------------------------------------------------------------------
-#define XCHG_TIMEOUT_NS 4000000000ull // a peer that has not published after 4 s is not going to
 
 __device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
 {
@@ -827,7 +831,9 @@ __device__ void xchg_publish(const PaprPeers &pp, int kind, size_t field_off, co
 }
 
 // All threads of ONE CTA: wait until every rank's publication `seq` of `kind` has landed in the own
-// window.  Returns false if a peer did not show up in time (the caller reports it, nothing hangs).
+// window.  Returns false if a peer did not show up within pp.timeout_ns (tunable "xchg_timeout_s") or
+// some rank already gave up: the rank that times out raises its abort word in EVERY window before it
+// returns, so a peer that arrives late finds it and fails as well - all ranks agree on the outcome.
 __device__ bool xchg_wait(const PaprPeers &pp, int kind, u64 seq)
 {
     __shared__ int s_late;
@@ -835,14 +841,18 @@ __device__ bool xchg_wait(const PaprPeers &pp, int kind, u64 seq)
     __syncthreads();
     if ((int)threadIdx.x < pp.world) {
         const u64 *f = &pp.win[pp.rank]->flag[kind][threadIdx.x];
+        const u64 *ab = &pp.win[pp.rank]->abort[threadIdx.x];
         const u64 t0 = global_timer_ns();
         while (ld_acquire_sys(f) < seq) {
-            if (global_timer_ns() - t0 > XCHG_TIMEOUT_NS) { atomicExch(&s_late, 1); break; }
+            if (ld_volatile(ab) != 0 || global_timer_ns() - t0 > pp.timeout_ns) { atomicExch(&s_late, 1); break; }
             __nanosleep(200);
         }
+        if (ld_volatile(ab) != 0) atomicExch(&s_late, 1);
     }
     __syncthreads();
-    return s_late == 0;
+    const bool late = s_late != 0;
+    if (late && (int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->abort[pp.rank], seq);
+    return !late;
 }
 
 // fused mode, sharded: fold this GPU's presample triples, publish them, wait for the other ranks',
@@ -911,22 +921,36 @@ void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, u64 n, P
     papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq);
 }
 
-// sharded: publish this shard's level counts (+ status word), collect every rank's, add them up
-__global__ void __launch_bounds__(1024) papr_counts_x_kernel(u64 *counts, PaprPlan *plan, PaprPeers pp, u64 seq)
+// sharded: publish this shard's level counts (+ status word), collect every rank's, add them up.
+// Only the L levels in use (and the status word) travel; buffer seq & 1 of the slot is written, so a
+// second publication within one analysis (exact redo after a fused miss) cannot race with a peer that
+// is still summing the first.
+__global__ void __launch_bounds__(1024) papr_counts_x_kernel(u64 *counts, const PaprDevLevels *lv, PaprPlan *plan,
+                                                             PaprPeers pp, u64 seq)
 {
-    xchg_publish(pp, XK_COUNTS, offsetof(PaprXchgSlot, counts), counts, PAPR_MAX_LEVELS + 1, seq);
+    const int L = min(max(lv->L, 0), PAPR_MAX_LEVELS), buf = (int)(seq & 1);
+    const size_t off = offsetof(PaprXchgSlot, counts) + (size_t)buf * sizeof(u64) * (PAPR_MAX_LEVELS + 1);
+    for (int r = 0; r < pp.world; ++r) {
+        u64 *dst = reinterpret_cast<u64 *>(reinterpret_cast<char *>(&pp.win[r]->slot[pp.rank]) + off);
+        for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = counts[i];
+        if (threadIdx.x == 0) dst[PAPR_MAX_LEVELS] = counts[PAPR_MAX_LEVELS];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->flag[XK_COUNTS][pp.rank], seq);
     const bool ok = xchg_wait(pp, XK_COUNTS, seq);
     if (!ok && threadIdx.x == 0) plan->pad = 1;
     for (int i = threadIdx.x; i <= PAPR_MAX_LEVELS; i += blockDim.x) {
+        if (i >= L && i != PAPR_MAX_LEVELS) continue;
         u64 acc = 0;
-        for (int q = 0; q < pp.world; ++q) acc += ld_volatile(&pp.win[pp.rank]->slot[q].counts[i]);
+        for (int q = 0; q < pp.world; ++q) acc += ld_volatile(&pp.win[pp.rank]->slot[q].counts[buf][i]);
         counts[i] = acc;
     }
 }
 
-void papr_launch_counts_x(u64 *counts, PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)
+void papr_launch_counts_x(u64 *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)
 {
-    papr_counts_x_kernel<<<1, 1024, 0, s>>>(counts, plan, pp, seq);
+    papr_counts_x_kernel<<<1, 1024, 0, s>>>(counts, lv, plan, pp, seq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1044,8 +1068,8 @@ void papr_launch_find_nan(const float *iq, u64 nsamples, u64 first_index, u64 *o
 // sum differs from it in the last bits.  Within one binade of the running sum (ulp u = 2^(k-52)) the
 // state is an integer m = sum/u and adding v = (q + f)*u gives m' = m + q + r, where r = 1 iff f > 1/2,
 // or f == 1/2 and m+q is odd - so the effect of a run of samples depends on the entry state only
-// through its PARITY.  A run is therefore a pair (D0, D1): the total increment for an even / odd entry
-// state.  Runs compose associatively (C.Dp = A.Dp + B.D[(p + A.Dp) & 1]), which makes the sequential
+// through its PARITY.  A run is therefore a pair (E0, E1): the total increment for an even / odd entry
+// state.  Runs compose associatively (C.Ep = A.Ep + B.E[parity after A]), which makes the sequential
 // sum a parallel reduction - exact as long as the running sum stays inside the binade, which the
 // host guarantees per tile from (approximate) prefix sums and re-checks when it chains the tiles.
 // Tiles that may cross a power of two are replayed on the host with real double adds.
@@ -1084,41 +1108,30 @@ void papr_launch_tilesum(const float *iq, u64 nsamples, double *tile_sum, int gr
     papr_tilesum_kernel<<<grid, 1024, 0, s>>>(iq, nsamples, tile_sum);
 }
 
-struct SeqRun { u64 d0, d1; }; // increment (in ulps of the binade) for an even / odd entry state
+// A run = what a stretch of samples does to the running sum inside ONE binade [2^k, 2^(k+1)): the
+// increment for an even and for an odd entry state.  The hardware computes both: an accumulator that
+// starts at the bottom of the binade, 2^k (integer state 2^52: even) or 2^k + ulp (odd), has the ulp of
+// the real running sum and the parity of the hypothesis, so its IEEE adds round exactly like the
+// reference's `sum += value` does - ties to even included - for as long as it stays inside the binade.
+// Two DADDs per sample instead of an integer emulation.  An accumulator that leaves the binade only
+// grows from there, so the increment it reports is >= 2^k and the chain (seq_chain) rejects the run.
+struct SeqRun { double a0, a1; }; // accumulators: 2^k (+ ulp) + everything added so far
 
-__device__ __forceinline__ SeqRun seq_compose(const SeqRun &a, const SeqRun &b)
+__device__ __forceinline__ double seq_base(int k, int odd)
 {
-    SeqRun c;
-    c.d0 = a.d0 + ((a.d0 & 1) ? b.d1 : b.d0);
-    c.d1 = a.d1 + (((1 + a.d1) & 1) ? b.d1 : b.d0);
-    return c;
+    return __longlong_as_double(((long long)(k + 1023) << 52) | (long long)odd);
 }
 
-// One sample's effect on the two candidate states (even / odd entry), papr.c:104 in integer form.
-// The states m0 = d0 and m1 = 1 + d1 receive the same increment from every sample except a tie
-// (fraction exactly 1/2) met while they still differ by one: then the odd one rounds up, and they
-// either merge (gap 0) or end up two apart (gap 2) - and move in lockstep ever after.  So one running
-// increment d0 plus the gap (0, 1 or 2) describes both; d1 = d0 + gap - 1.
-__device__ __forceinline__ void seq_step(float v, int U, u64 &d0, unsigned &gap)
+__device__ __forceinline__ unsigned seq_lsb(double a) { return (unsigned)__double2loint(a) & 1u; }
+
+// run A followed by run B (both started from the bases c0 / c1 of the same binade)
+__device__ __forceinline__ SeqRun seq_compose(const SeqRun &a, const SeqRun &b, double c0, double c1)
 {
-    const unsigned b = __float_as_uint(v);
-    if (b == 0) return;
-    const unsigned e = b >> 23;
-    const unsigned M = e ? ((b & 0x7fffffu) | 0x800000u) : (b & 0x7fffffu); // v = M * 2^E
-    const int E = (int)(e ? e : 1u) - 150;
-    const int shift = U - E;
-    if (shift <= 0) {            // v is a whole number of ulps: exact add
-        d0 += (u64)M << (-shift);
-    } else if (shift <= 24) {    // q ulps plus a fraction f = rem / 2^shift
-        const u64 q = M >> shift;
-        const unsigned rem = M & ((1u << shift) - 1u), half = 1u << (shift - 1);
-        u64 r0 = rem > half ? 1u : 0u;
-        if (rem == half) {       // tie: to even
-            r0 = (d0 + q) & 1;
-            if (gap == 1) gap = r0 ? 0u : 2u;
-        }
-        d0 += q + r0;
-    }                            // shift >= 25: f < 1/2 and q = 0, the add rounds back
+    const double i0 = __dsub_rn(b.a0, c0), i1 = __dsub_rn(b.a1, c1); // B's increments: exact
+    SeqRun c;
+    c.a0 = __dadd_rn(a.a0, seq_lsb(a.a0) ? i1 : i0);
+    c.a1 = __dadd_rn(a.a1, seq_lsb(a.a1) ? i1 : i0);
+    return c;
 }
 
 // One CTA of SEQ_T threads per tile of PAPR_SEQ_TILE samples; thread t owns the SEQ_PER consecutive
@@ -1129,7 +1142,7 @@ __device__ __forceinline__ void seq_step(float v, int U, u64 &d0, unsigned &gap)
 #define SEQ_T 256
 #define SEQ_PER (PAPR_SEQ_TILE / SEQ_T) // 128 samples = 1 KiB per thread
 __global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64 nsamples, const short *tile_code,
-                                                           SeqRun *tile_run)
+                                                           double *tile_run)
 {
     __shared__ SeqRun s_w[SEQ_T / 32];
     const unsigned ntiles = (unsigned)((nsamples + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE);
@@ -1137,11 +1150,11 @@ __global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int k = tile_code[tile];
         if (k >= PAPR_SEQ_ZERO) continue; // zero or dirty tile: nothing to do here (uniform per CTA)
-        const int U = k - 52;             // exponent of the binade's ulp
+        const double c0 = seq_base(k, 0), c1 = seq_base(k, 1);
         const u64 s0 = (u64)tile * PAPR_SEQ_TILE + (u64)t * SEQ_PER;
         const float4 *p = reinterpret_cast<const float4 *>(iq + 2 * s0);
-        u64 d0 = 0;
-        unsigned gap = 1;
+        SeqRun r;
+        r.a0 = c0; r.a1 = c1;
         if (s0 + SEQ_PER <= nsamples) {
 #pragma unroll 1
             for (int j = 0; j < SEQ_PER / 2; j += 4) {
@@ -1149,32 +1162,34 @@ __global__ void __launch_bounds__(SEQ_T) papr_seqsum_kernel(const float *iq, u64
 #pragma unroll
                 for (int u = 0; u < 4; ++u) q[u] = __ldg(p + j + u);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    seq_step(power_of(q[u].x, q[u].y), U, d0, gap);
-                    seq_step(power_of(q[u].z, q[u].w), U, d0, gap);
+                for (int u = 0; u < 4; ++u) { // papr.c:103-104, twice: once per hypothesis
+                    const double v0 = (double)power_of(q[u].x, q[u].y), v1 = (double)power_of(q[u].z, q[u].w);
+                    r.a0 = __dadd_rn(__dadd_rn(r.a0, v0), v1);
+                    r.a1 = __dadd_rn(__dadd_rn(r.a1, v0), v1);
                 }
             }
         } else { // ragged end of the capture
             for (u64 s = s0; s < nsamples && s < s0 + SEQ_PER; ++s) {
                 const float2 h = *reinterpret_cast<const float2 *>(iq + 2 * s);
-                seq_step(power_of(h.x, h.y), U, d0, gap);
+                const double v = (double)power_of(h.x, h.y);
+                r.a0 = __dadd_rn(r.a0, v);
+                r.a1 = __dadd_rn(r.a1, v);
             }
         }
-        SeqRun r;
-        r.d0 = d0; r.d1 = d0 + gap - 1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { // ordered: lane l (multiple of 2o) <- l then l+o
             SeqRun nb;
-            nb.d0 = __shfl_down_sync(FULL, r.d0, o);
-            nb.d1 = __shfl_down_sync(FULL, r.d1, o);
-            r = seq_compose(r, nb); // only the lanes that are multiples of 2o keep a meaningful value
+            nb.a0 = __shfl_down_sync(FULL, r.a0, o);
+            nb.a1 = __shfl_down_sync(FULL, r.a1, o);
+            r = seq_compose(r, nb, c0, c1); // only the lanes that are multiples of 2o keep a meaningful value
         }
         if (lane == 0) s_w[warp] = r;
         __syncthreads();
         if (t == 0) {
             SeqRun acc = s_w[0];
-            for (int w = 1; w < SEQ_T / 32; ++w) acc = seq_compose(acc, s_w[w]);
-            tile_run[tile] = acc;
+            for (int w = 1; w < SEQ_T / 32; ++w) acc = seq_compose(acc, s_w[w], c0, c1);
+            tile_run[2 * tile] = __dsub_rn(acc.a0, c0);     // increment for an even entry state
+            tile_run[2 * tile + 1] = __dsub_rn(acc.a1, c1); // ... and for an odd one
         }
         __syncthreads();
     }
@@ -1185,5 +1200,5 @@ int papr_seqsum_configure(void) { return 0; } // no dynamic shared memory any mo
 void papr_launch_seqsum(const float *iq, u64 nsamples, const short *tile_code, void *tile_run, int grid,
                         cudaStream_t s)
 {
-    papr_seqsum_kernel<<<grid, SEQ_T, 0, s>>>(iq, nsamples, tile_code, reinterpret_cast<SeqRun *>(tile_run));
+    papr_seqsum_kernel<<<grid, SEQ_T, 0, s>>>(iq, nsamples, tile_code, reinterpret_cast<double *>(tile_run));
 }

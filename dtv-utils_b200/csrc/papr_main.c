@@ -72,22 +72,16 @@ int papr_main(int argc, char **argv)
     papr_result *r = (papr_result *)calloc(1, sizeof(*r));
     int ndev = (v = getenv("PAPR_B200_DEVICES")) ? atoi(v) : 1; /* GPUs to shard the capture over */
     if (ndev < 1) ndev = 1;
-    /* CUDA initialisation time grows with the number of visible GPUs (seconds on an 8-GPU box):
-     * expose only the ones this run uses, unless the user already restricted them */
-    if (!getenv("CUDA_VISIBLE_DEVICES")) {
-        char list[256];
-        int pos = 0, first = (v = getenv("PAPR_B200_DEVICE")) ? atoi(v) : 0;
-        for (int d = 0; d < ndev && pos < 240; d++) pos += snprintf(list + pos, sizeof(list) - pos, d ? ",%d" : "%d", first + d);
-        setenv("CUDA_VISIBLE_DEVICES", list, 1);
-        setenv("PAPR_B200_DEVICE", "0", 1);
-    }
     if (ndev > 1) {
         papr_multi *m = NULL;
         /* stdout belongs to the reference's text: keep any NCCL banner / debug output off it */
         setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
         if ((v = getenv("NCCL_DEBUG")) && strcasecmp(v, "VERSION") == 0)
             setenv("NCCL_DEBUG", "WARN", 1); /* the VERSION level ignores NCCL_DEBUG_FILE and prints on stdout */
-        if (papr_multi_create(ndev, NULL, &m) != PAPR_OK) {
+        int devs[64], first = (v = getenv("PAPR_B200_DEVICE")) ? atoi(v) : 0; /* first GPU of the run */
+        if (ndev > 64) ndev = 64;
+        for (int d = 0; d < ndev; d++) devs[d] = first + d;
+        if (papr_multi_create(ndev, devs, &m) != PAPR_OK) {
             fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_multi_last_error(NULL));
             free(r);
             return 1;
