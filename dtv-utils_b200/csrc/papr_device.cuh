@@ -64,6 +64,8 @@ struct PaprPlan {
     float window;       // fused mode: relative half-width of the threshold windows
     int pad;            // peer-memory exchange: 1 = a peer's publication did not arrive in time
     double avg_pred;    // fused mode: predicted mean power
+    double wcv;         // fused mode: sigmas x relative std of one warp batch's power sum (how far the sum
+                        // of the first g samples may stray from g x avg_pred: wcv / sqrt(g / batch))
 };
 
 struct PaprDevLevels {
@@ -89,6 +91,66 @@ struct PaprScanArgs {
     unsigned long long *g_hist;    // [PAPR_NCELLS_MAX]
     unsigned long long *g_fine;    // [n_amb << sh]
     unsigned long long *g_over;    // samples above the cell range
+};
+
+// ---- the reference's SEQUENTIAL double sum (papr.c:104) inside the fused scan (papr_exact.cu) -------
+// The TMA-fed scan gives every lane 8 consecutive samples per warp batch and every warp whole "tiles"
+// of 16 batches; per tile it emits a RUN - the increment of the running sum for an even and for an odd
+// entry state, valid inside one binade [2^k, 2^(k+1)) of the running sum (see papr_seqsum_kernel).  k is
+// predicted per tile from the presample mean; tiles that may straddle a power of two carry one run per
+// candidate binade and per batch ("multi" tiles).  A single-CTA kernel then chains everything in file
+// order, resolving each binade crossing down to the 8 samples in which it happens.
+#define XT_TILE_BATCHES 16
+#define XT_TILE_SAMPLES (XT_TILE_BATCHES * PAPR_BATCH_SAMPLES) // 4096 samples = 32 KiB per warp tile
+#define XT_SUPER_TILES PAPR_WARPS                              // 32 tiles = 1 MiB per CTA iteration
+#define XT_SUPER_SAMPLES (XT_SUPER_TILES * XT_TILE_SAMPLES)
+#define XT_MAX_CAND 4                                          // candidate binades of a multi tile
+#define XT_KBIAS 1100                                          // tile code: k + XT_KBIAS in bits 0-11 ...
+#define XT_CODE_NC(c) (((c) >> 12) & 7)                        // ... candidates in bits 12-14 (0 = none) ...
+#define XT_CODE_LITERAL 0x8000                                 // ... bit 15: summed literally, e0 = exit state ...
+#define XT_CODE_SLOT(c) ((unsigned)(c) >> 16)                  // ... bits 16-31: slot in the multi log
+#define XT_CODE_K(c) (((c) & 0xfff) - XT_KBIAS)
+#define XT_MAX_ITEMS 224                                       // chain items per shard
+#define XT_MAX_CROSS 48                                        // binade crossings per shard (a double has 2046 binades;
+                                                               // a shard of 2^36 samples passes < 40 above its first tile)
+
+struct PaprTileRun { double e0, e1; };                         // increments for an even / odd entry state
+
+struct PaprSuperRec {                                          // 32 tiles composed (papr_xt_compose_kernel)
+    double e0, e1;
+    double asum;                                               // approximate sum of the super-tile's powers
+    int code;                                                  // k + XT_KBIAS if all tiles share one binade, XT_SUPER_*
+    int pad;
+};
+enum { XT_SUPER_COMPLEX = -1, XT_SUPER_EMPTY = -2 };
+
+struct PaprExactArgs {
+    unsigned long long g_first;    // whole-capture index of this launch's sample 0 (prediction of the running sum)
+    unsigned tile_base;            // index of this launch's first tile in the shard's tile arrays
+    int literal_tile0;             // 1: this launch starts the capture (running sum exactly 0): tile 0 is summed literally
+    PaprTileRun *tile_run;         // [ntiles]
+    int *tile_code;                // [ntiles]
+    PaprTileRun *multi;            // [multi_cap][XT_MAX_CAND][XT_TILE_BATCHES] per-batch runs of the multi tiles
+    unsigned *multi_count;
+    unsigned multi_cap;
+};
+
+// what the chain of one shard boils down to: a short list of items applied in order to the running sum
+enum { XT_IT_SEG = 1, XT_IT_LIT = 2, XT_IT_ABS = 3 };
+struct PaprChainItem {
+    int type;       // SEG: a run (d[0], d[1]) valid in binade k; LIT: 8 powers added literally, ending in binade k;
+    int k;          // ABS: the running sum becomes d[0] (valid for an entry state of exactly 0)
+    double d[8];
+};
+enum { XT_OK = 0, XT_FALLBACK = 1, XT_NONFINITE = 2 };
+struct PaprChainList {
+    int n;
+    int status;     // XT_*
+    int why;        // diagnostic: which check sent the chain to the fall-back
+    int pad;
+    double approx;  // approximate sum of the shard (what the tree sum used to be)
+    double exact;   // (after the walk) the running sum after this shard
+    PaprChainItem item[XT_MAX_ITEMS];
 };
 
 // ---- peer-memory exchange between the ranks of one box (NVLink, cudaIpc-mapped windows) -----------
@@ -133,7 +195,8 @@ void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, unsigned lo
                                 cudaStream_t s);
 void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
                                  PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
-                                 unsigned long long *status_word, cudaStream_t s);
+                                 unsigned long long *status_word, const PaprChainList *chain /* or NULL */,
+                                 int *chain_report /* {status, why} or NULL */, cudaStream_t s);
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
                         PaprDevStats *merged, PaprDevLevels *lv, unsigned long long *status_word, cudaStream_t s);
 void papr_launch_presample(const float *iq, unsigned long long nsamples, int stride, int grid,
@@ -169,5 +232,13 @@ void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned
                                    unsigned long long seq, cudaStream_t s);
 void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
                           unsigned long long seq, cudaStream_t s);
+int papr_scan_tma_configure(void);
+void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, const PaprScanArgs &a, const PaprExactArgs &x,
+                          cudaStream_t s);
+void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi,
+                            PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s);
+void papr_launch_xt_chain(const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
+                          const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
+                          PaprChainList *out /* two lists back to back: [0] result, [1] scratch */, cudaStream_t s);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

@@ -8,6 +8,7 @@
 // end: the reference's scalar epilogue (papr.c:131-141 / 164-173) is evaluated on the device from
 // host-libm tables (papr_levels_kernel), then re-evaluated on the host with the real libm and
 // compared bit for bit before anything is reported.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -71,6 +72,8 @@ struct DevOut {
     PaprPlan plan;
     u64 counts[PAPR_MAX_LEVELS + 1]; // [PAPR_MAX_LEVELS] = status word (RES_* bits, summed over ranks)
     PaprDevLevels lv;
+    int chain[2];                    // {XT_* status, why} of the sequential sum chained on the device
+    int chain_pad[2];
 };
 
 struct HostOut {
@@ -209,7 +212,7 @@ struct papr_engine {
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
-    int exact_sum = -1;       // -1: on for the file/host path, off for device-resident; 0 off; 1 on
+    int exact_sum = -1;       // != 0 (default): the reference's sequential double sum, bit for bit, on every path; 0: off
     // exact sequential-sum scratch (grown on demand)
     u64 seq_tiles = 0;
     double *d_tile_sum = nullptr, *h_tile_sum = nullptr;
@@ -219,6 +222,15 @@ struct papr_engine {
     unsigned seq_dirty = 0;
     const float *seq_sums_ptr = nullptr; // h_tile_sum currently holds the tile sums of this resident shard ...
     u64 seq_sums_n = 0;                  // ... of this many samples (computed under the H2D shadow)
+    // sequential sum inside the fused scan (papr_exact.cu): tile runs, super-tile records, multi-tile log, chain
+    u64 xt_tiles = 0;
+    unsigned xt_multi_cap = 8192;
+    PaprTileRun *d_xt_run = nullptr, *d_xt_multi = nullptr, *d_xt_multi_tile = nullptr;
+    int *d_xt_code = nullptr;
+    PaprSuperRec *d_xt_super = nullptr;
+    unsigned *d_xt_multi_count = nullptr;
+    PaprChainList *d_xt_chain = nullptr; // [0] result, [1] scratch
+    int xt_status = -1, xt_why = 0;      // of the last analysis (-1: the device chain did not run)
     // device work buffers
     int grid = 0;
     DevWork *d_work = nullptr;
@@ -314,7 +326,7 @@ static int engine_init(papr_engine *e, int device)
     e->num_sms = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    if (papr_scan_configure() != 0 || papr_seqsum_configure() != 0)
+    if (papr_scan_configure() != 0 || papr_seqsum_configure() != 0 || papr_scan_tma_configure() != 0)
         return fail(e, PAPR_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed");
     e->grid = e->num_sms * e->grid_per_sm;
     if (e->grid > kMaxGrid) return fail(e, PAPR_ERR_CUDA, "more SMs than this build supports");
@@ -328,6 +340,11 @@ static int engine_init(papr_engine *e, int device)
     CU(cudaMalloc(&e->d_pre4, sizeof(double) * 4));
     CU(cudaMalloc(&e->d_tables, sizeof(double) * 4 * PAPR_MAX_LEVELS));
     CU(cudaHostAlloc(&e->h_out, sizeof(HostOut), cudaHostAllocDefault));
+    CU(cudaMalloc(&e->d_xt_multi, sizeof(PaprTileRun) * (size_t)e->xt_multi_cap * XT_MAX_CAND * XT_TILE_BATCHES));
+    CU(cudaMalloc(&e->d_xt_multi_tile, sizeof(PaprTileRun) * (size_t)e->xt_multi_cap * XT_MAX_CAND));
+    CU(cudaMalloc(&e->d_xt_multi_count, sizeof(unsigned)));
+    CU(cudaMalloc(&e->d_xt_chain, 2 * sizeof(PaprChainList)));
+    CU(cudaMemset(e->d_xt_chain, 0, 2 * sizeof(PaprChainList)));
     {
         std::vector<double> t(4 * PAPR_MAX_LEVELS, INFINITY);
         papr_host_build_tables(0, kLevels1dB, &t[0], &t[2 * PAPR_MAX_LEVELS]);
@@ -372,6 +389,8 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (e->h_tile_run) cudaFreeHost(e->h_tile_run);
     if (e->h_tile_data) cudaFreeHost(e->h_tile_data);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
+    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super); cudaFree(e->d_xt_multi); cudaFree(e->d_xt_multi_tile);
+    cudaFree(e->d_xt_multi_count); cudaFree(e->d_xt_chain);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_stage[0]) cudaFreeHost(e->h_stage[0]);
     for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
@@ -455,11 +474,100 @@ static int enqueue_scan(papr_engine *e, bool stats, bool hist, const float *d_iq
     return PAPR_OK;
 }
 
+// ---- the TMA-fed fused scan with the sequential sum inside (papr_exact.cu) ------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess) { cudaGetLastError(); p = nullptr; }
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+
+static int ensure_xt_buffers(papr_engine *e, u64 ntiles)
+{
+    if (ntiles <= e->xt_tiles) return PAPR_OK;
+    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super);
+    e->d_xt_run = nullptr; e->d_xt_code = nullptr; e->d_xt_super = nullptr;
+    e->xt_tiles = 0;
+    const u64 cap = std::max<u64>(ntiles, 1u << 16);
+    CU(cudaMalloc(&e->d_xt_run, cap * sizeof(PaprTileRun)));
+    CU(cudaMalloc(&e->d_xt_code, cap * sizeof(int)));
+    CU(cudaMalloc(&e->d_xt_super, (cap / XT_SUPER_TILES + 1) * sizeof(PaprSuperRec)));
+    e->xt_tiles = cap;
+    return PAPR_OK;
+}
+
+// is the fused scan with the in-sweep sequential sum applicable to this shard?
+static bool xt_applicable(const papr_engine *e, u64 n)
+{
+    return e->exact_sum != 0 && n >= 2 * XT_TILE_SAMPLES && tensor_map_encoder() != nullptr;
+}
+
+// the whole shard in launches of <= 2^31 samples (tile-aligned cuts); g_first = whole-capture index of sample 0
+static int enqueue_scan_tma(papr_engine *e, const float *d_iq, u64 n, u64 first, bool timed)
+{
+    int rc;
+    const u64 ntiles = (n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES;
+    if ((rc = ensure_xt_buffers(e, ntiles))) return rc;
+    CU(cudaMemsetAsync(e->d_xt_multi_count, 0, sizeof(unsigned), e->stream));
+    if (timed && e->scan_pairs < 2) CU(cudaEventRecord(e->ev_scan[2 * e->scan_pairs], e->stream));
+    for (u64 off = 0, m = 0; off < n; off += m) {
+        m = std::min(kMaxLaunchSamples, n - off);
+        if (n - off - m < 2 * XT_TILE_SAMPLES) m = n - off; // never leave a sliver (a launch needs whole 128-byte rows)
+        PaprScanArgs a;
+        scan_args(e, a, d_iq + 2 * off, m, first + off);
+        PaprExactArgs x;
+        x.g_first = first + off;
+        x.tile_base = (unsigned)(off / XT_TILE_SAMPLES);
+        x.literal_tile0 = first + off == 0;
+        x.tile_run = e->d_xt_run; x.tile_code = e->d_xt_code;
+        x.multi = e->d_xt_multi; x.multi_count = e->d_xt_multi_count; x.multi_cap = e->xt_multi_cap;
+        CUtensorMap tm; // rows of 128 bytes (16 samples); the < 16 samples past the last full row are patched in by the kernel
+        const cuuint64_t dims[2] = {32, std::max<u64>(m / 16, 1)};
+        const cuuint64_t strides[1] = {128};
+        const cuuint32_t box[2] = {32, 16}, es[2] = {1, 1};
+        CUresult r = tensor_map_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(d_iq + 2 * off), dims, strides, box, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(e, PAPR_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+        papr_launch_scan_tma(&tm, e->grid, a, x, e->stream);
+        e->launches += 1;
+    }
+    if (timed && e->scan_pairs < 2) {
+        CU(cudaEventRecord(e->ev_scan[2 * e->scan_pairs + 1], e->stream));
+        e->scan_pairs++;
+    }
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
+// tile runs -> super-tile records -> the chained sum (d_xt_chain[0]: status, exact)
+static int enqueue_xt_chain(papr_engine *e, const float *d_iq, u64 n)
+{
+    const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
+    const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
+    papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi, e->d_xt_multi_tile, e->d_xt_super,
+                           (int)std::min<unsigned>((nsuper + 7) / 8, (unsigned)e->num_sms * 8), e->stream);
+    papr_launch_xt_chain(e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles, d_iq, n,
+                         e->d_xt_chain, e->stream);
+    e->launches += 2;
+    CU(cudaGetLastError());
+    return PAPR_OK;
+}
+
 // CTA partials -> local stats -> (single shard) merged stats, avg, L, levels on the device
-static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph)
+static int enqueue_finalize_levels(papr_engine *e, u64 n, int graph, bool chained = false)
 {
     papr_launch_finalize_levels(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
+                                &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], chained ? e->d_xt_chain : nullptr,
+                                chained ? e->d_out->chain : nullptr, e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
     return PAPR_OK;
@@ -894,10 +1002,12 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if (mode == PAPR_MODE_AUTO) // fused pays off once the subsample is a small fraction of the shard
         mode = (n >= e->fused_min_samples && stride >= 8) ? PAPR_MODE_FUSED : PAPR_MODE_TWO_PASS;
     out->mode_used = mode;
-    const bool exact = e->exact_sum == 1;
+    const bool exact = e->exact_sum != 0; // papr.c:104 bit for bit (tunable "exact_sum" = 0: any deterministic order)
     int rc;
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
+    const bool chained = mode == PAPR_MODE_FUSED && xt_applicable(e, n); // sequential sum inside the sweep
+    e->xt_status = -1;
     if (mode == PAPR_MODE_FUSED) {
         papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES), stride,
                               e->grid, e->d_pre_cta, e->stream);
@@ -905,8 +1015,14 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
                               1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
         papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
         e->launches += 3;
-        if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
-        if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
+        if (chained) {
+            if ((rc = enqueue_scan_tma(e, d_iq, n, 0, true))) return rc;
+            if ((rc = enqueue_xt_chain(e, d_iq, n))) return rc;
+            if ((rc = enqueue_finalize_levels(e, n, graph, true))) return rc;
+        } else {
+            if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
+            if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
+        }
         if ((rc = enqueue_resolve(e))) return rc;
     } else {
         if ((rc = enqueue_scan(e, true, false, d_iq, n, 0, true))) return rc;
@@ -917,6 +1033,17 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     stats_to_host(e->h_out->o.merged, &out->stats);
+    if (chained) {
+        e->xt_status = e->h_out->o.chain[0];
+        e->xt_why = e->h_out->o.chain[1];
+        if (e->xt_status == XT_FALLBACK) { // the device chain could not vouch for its sum: the two-sweep emulation
+            double s = 0.0;
+            if ((rc = exact_sequential_sum(e, d_iq, n, &s)) < 0) return rc;
+            if (rc == 0) out->stats.sum = s; // levels are re-derived from it below; counts redone only if they move
+        }
+    }
+    if (chained) out->sum_path = e->xt_status == XT_OK ? 1u : e->xt_status == XT_FALLBACK ? (2u | ((unsigned)e->xt_why << 8)) : 0u;
+    else out->sum_path = exact && std::isfinite(out->stats.sum) ? 2u : 0u;
     if ((rc = fix_nan_sign(e, d_iq, n, 0, &out->stats))) return rc;
     if (collect(e, graph, out, true)) {
         out->fused_miss = mode == PAPR_MODE_FUSED;

@@ -1,0 +1,839 @@
+// papr_exact.cu — the fused scan of a device-resident shard, fed by TMA, with the reference's
+// SEQUENTIAL double sum (drmpeg/dtv-utils papr.c:104, `sum += value` in file order, rounding to
+// nearest-even at every add) emulated bit for bit inside the same sweep.
+//
+//   papr_scan_tma_kernel   papr.c:100-129 + 143-153 in one pass, like papr_scan_kernel<1,1>, but the samples
+//                          arrive through 2-D TMA boxes (16 rows x 128 B = one 2 KiB warp batch, 128-byte
+//                          swizzle) so that every lane reads a run of 8 CONSECUTIVE samples without bank
+//                          conflicts, and every warp owns whole tiles of 16 consecutive batches.
+//                          Per lane and batch two DADD accumulators (even / odd entry state, anchored
+//                          at the bottom of the predicted binade of the running sum) do the rounding
+//                          exactly as the reference's adds do; two ballots carry the parity from lane to
+//                          lane; per-lane totals are folded once per tile.
+//   papr_xt_compose_kernel 32 tile runs -> one super-tile run (ordered, associative composition)
+//   papr_xt_chain_kernel   one CTA: approximate prefix sums locate every binade crossing of the running
+//                          sum down to 8 samples; the stretches between crossings are composed in
+//                          parallel; what remains is a list of < 100 items applied in order.
+// Everything is verified while it is applied (state inside the assumed binade before and after each run);
+// a failed check only ever sends the analysis to the slower two-sweep emulation, never to a wrong sum.
+#include <cuda.h>
+
+#include "papr_scan_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xt_base(int k, unsigned odd) // 2^k, or 2^k + one ulp
+{
+    return __longlong_as_double(((long long)(k + 1023) << 52) | (long long)odd);
+}
+
+__device__ __forceinline__ unsigned xt_lsb(double a) { return (unsigned)__double2loint(a) & 1u; }
+
+// floor(log2(x)) of a positive normal double; -4000 for zero / denormals / negatives, +4000 for Inf / NaN
+__device__ __forceinline__ int xt_expo(double x)
+{
+    const long long b = __double_as_longlong(x);
+    const int e = (int)((b >> 52) & 0x7ff);
+    if (b <= 0 || e == 0) return -4000;
+    if (e == 0x7ff) return 4000;
+    return e - 1023;
+}
+
+__device__ __forceinline__ PaprTileRun xt_compose(const PaprTileRun &a, const PaprTileRun &b, int k)
+{
+    // parity of the state after A: bit 0 of (base + increment); exact while A stays inside the binade, and
+    // an A that left it keeps e >= 2^k whatever is added (increments are >= 0), which the walk rejects
+    const unsigned p0 = xt_lsb(__dadd_rn(xt_base(k, 0), a.e0)), p1 = xt_lsb(__dadd_rn(xt_base(k, 1), a.e1));
+    PaprTileRun c;
+    c.e0 = __dadd_rn(a.e0, p0 ? b.e1 : b.e0);
+    c.e1 = __dadd_rn(a.e1, p1 ? b.e1 : b.e0);
+    return c;
+}
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
+{
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+}
+
+// one 2 KiB box: rows [row, row+16) x 128 B of the capture -> swizzled shared memory, completion on `bar`
+__device__ __forceinline__ void tma_batch(unsigned dst, const CUtensorMap *tm, int row, unsigned bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(0), "r"(row), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(unsigned addr)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+
+// byte offset of sample i (0..255) of a batch inside its swizzled 2 KiB box
+__device__ __forceinline__ unsigned xt_sample_off(unsigned i)
+{
+    const unsigned row = i >> 4, chunk = (i >> 1) & 7;
+    return row * 128u + ((chunk ^ (row & 7u)) << 4) + (i & 1u) * 8u;
+}
+
+// Candidate binades of the running sum while samples [g0, g1) of the whole capture are added, from the
+// presample's mean and its uncertainty.  Returns the number of candidates (0 = cannot tell), first in *k_lo.
+__device__ __forceinline__ int xt_candidates(double avg, double window, double wcv, unsigned long long g0,
+                                             unsigned long long g1, int *k_lo)
+{
+    if (!(avg > 0.0) || g0 == 0) return 0;
+    const double w = window + wcv * rsqrt((double)g0 * (1.0 / PAPR_BATCH_SAMPLES));
+    const double lo = avg * (double)g0 * (1.0 - w), hi = avg * (double)g1 * (1.0 + w);
+    const int a = xt_expo(lo), b = xt_expo(hi);
+    if (a <= -4000 || b >= 4000 || b - a >= XT_MAX_CAND) return 0;
+    *k_lo = a;
+    return b - a + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused scan
+// ------------------------------------------------------------------------------------------------
+#define XT_RING_BYTES (PAPR_WARPS * 2048)
+#define XT_SMEM_BYTES (SCAN_SMEM_BYTES + 1024 + XT_RING_BYTES)
+
+// entry parity of this lane's run given the exit parities of the lower lanes (b0 / b1: ballots of the exit
+// parity for an even / odd entry) and the parity P with which the batch is entered
+struct XtLink {
+    unsigned flip, fixed, base; // parity = (fixed ? base : P) ^ flip
+};
+
+__device__ __forceinline__ XtLink xt_link(unsigned b0, unsigned b1, unsigned lt)
+{
+    const unsigned c = ~(b0 ^ b1); // lanes whose exit parity does not depend on how they were entered
+    const unsigned ng = b0 & ~b1;  // the others either pass the parity on (0,1) or invert it (1,0): these invert
+    const unsigned cm = c & lt;
+    const unsigned upto = cm ? (0xffffffffu >> __clz(cm)) : 0u; // lanes 0..j, j = nearest such lane below
+    XtLink l;
+    l.fixed = cm != 0;
+    l.base = (b0 & (upto ^ (upto >> 1))) != 0; // exit parity of lane j
+    l.flip = __popc(ng & lt & ~upto) & 1u;
+    return l;
+}
+
+__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                        const PaprScanArgs a, const PaprExactArgs x)
+{
+    ScanState<true, true> st;
+    __shared__ __align__(8) unsigned long long s_bar[PAPR_WARPS];
+    unsigned *s_hist = reinterpret_cast<unsigned *>(scan_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+
+    const PaprPlan pl = *a.plan;
+    const bool do_hist = (pl.status & PLAN_HIST) != 0;
+    {
+        unsigned *s_fb = s_hist + (PAPR_NCELLS_MAX + 2);
+        st.g_fine = a.g_fine;
+        asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
+                     : "=r"(st.smem_slot1) : "l"(s_hist + 1));
+        st.sh = pl.sh;
+        st.cell_base = do_hist ? pl.cell_base : 0x7fffffff; // no valid plan: every sample lands in slot 0
+        st.ncells = do_hist ? pl.ncells : 0;
+        st.fmask = (1u << pl.sh) - 1u;
+        for (int i = threadIdx.x; i < st.ncells + 2; i += PAPR_THREADS) {
+            s_hist[i] = 0;
+            s_fb[i] = (i >= 1 && i <= st.ncells) ? a.fine_base[i - 1] : 0u;
+        }
+    }
+    st.upd = 0;
+#pragma unroll
+    for (int t = 0; t < PAPR_NTRACK; ++t) {
+        st.run_val[t] = a.wp[blockIdx.x].val[t];
+        st.run_pos[t] = 0;
+    }
+    const unsigned ring = (smem_u32(scan_smem) + SCAN_SMEM_BYTES + 1023u) & ~1023u;
+    const unsigned my = ring + warp * 2048u, bar = smem_u32(&s_bar[warp]);
+    if (lane == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // this lane's run: samples 8*lane .. 8*lane+7 of the batch = half a 128-byte row
+    unsigned off[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const unsigned row = lane >> 1, c = 4u * (lane & 1) + u;
+        off[u] = my + row * 128u + ((c ^ (row & 7u)) << 4);
+    }
+
+    const u64 n = a.nsamples;
+    const unsigned nbatch = (unsigned)((n + PAPR_BATCH_SAMPLES - 1) / PAPR_BATCH_SAMPLES);
+    const unsigned ntiles = (nbatch + XT_TILE_BATCHES - 1) / XT_TILE_BATCHES;
+    const unsigned full_rows = (unsigned)(n >> 4), tail_n = (unsigned)(n & 15); // the tensor map covers the full rows
+    const unsigned tstride = gridDim.x * XT_SUPER_TILES;
+    unsigned phase = 0;
+    double wsum = 0.0; // lane 0: approximate sum of this warp's tiles (what the tree sum used to be)
+
+    unsigned tile = blockIdx.x * XT_SUPER_TILES + warp;
+    if (tile < ntiles && lane == 0) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 16), bar);
+    for (; tile < ntiles; tile += tstride) {
+        // ---- which binade(s) will the running sum be in while this tile is added?
+        const u64 g0 = x.g_first + (u64)tile * XT_TILE_SAMPLES;
+        int k_lo = 0;
+        int nc = xt_candidates(pl.avg_pred, (double)pl.window, pl.wcv, g0, g0 + XT_TILE_SAMPLES, &k_lo);
+        const bool literal = x.literal_tile0 && g0 == 0;
+        unsigned slot = 0;
+        if (nc > 1) {
+            if (lane == 0) slot = atomicAdd(x.multi_count, 1u);
+            slot = __shfl_sync(FULL, slot, 0);
+            if (slot >= x.multi_cap) nc = 0; // log full: the chain falls back if this tile matters
+        }
+        double A0 = 0.0, A1 = 0.0;   // nc == 1: this lane's share of the tile's increment, even / odd tile entry
+        unsigned P0 = 0, P1 = 1;     //          parity of the running state under the two hypotheses
+        double aux = 0.0;            // lane 0 (multi / literal) or every lane (unknown): approximate sum
+        const double c0 = xt_base(k_lo, 0), c1 = xt_base(k_lo, 1);
+        const unsigned b_first = tile * XT_TILE_BATCHES;
+        const unsigned nb = min((unsigned)XT_TILE_BATCHES, nbatch - b_first);
+        for (unsigned b = 0; b < nb; ++b) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            const unsigned row0 = (b_first + b) * 16u;
+            if (tail_n && full_rows >= row0 && full_rows < row0 + 16u) { // < 16 samples past the last full row
+                if ((unsigned)lane < tail_n) {
+                    const u64 s = ((u64)full_rows << 4) + lane;
+                    const float2 h = *reinterpret_cast<const float2 *>(a.iq + 2 * s);
+                    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(my + xt_sample_off((unsigned)(s & 255))), "f"(h.x), "f"(h.y) : "memory");
+                }
+                __syncwarp();
+            }
+            float4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = lds128(off[u]);
+            if (literal) { // papr.c:103-104 as written, from a running sum of exactly 0
+                if (lane == 0) {
+                    for (unsigned i = 0; i < PAPR_BATCH_SAMPLES; ++i) {
+                        float2 h;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "r"(my + xt_sample_off(i)));
+                        aux = __dadd_rn(aux, (double)power_of(h.x, h.y));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { // the buffer is free again: fetch the next batch (of this tile or of the next one)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the warp's reads above vs the TMA write below
+                if (b + 1 < nb) tma_batch(my, &tmap, (int)(row0 + 16u), bar);
+                else if (tile + tstride < ntiles) tma_batch(my, &tmap, (int)((tile + tstride) * XT_TILE_BATCHES * 16), bar);
+            }
+
+            // ---- per-sample work: power, extremes, CCDF cells
+            float v[8];
+            float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 q = r[u];
+                v[2 * u] = power_of(q.x, q.y);
+                v[2 * u + 1] = power_of(q.z, q.w);
+                bm0 = fmaxf(bm0, fmaxf(v[2 * u], v[2 * u + 1]));
+                bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
+                bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
+                bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
+                bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
+                hist_pair(st, v[2 * u], v[2 * u + 1]);
+            }
+            {
+                const bool cand = __float_as_int(bm0) > st.run_val[TR_PEAK] || __float_as_int(bm1) > st.run_val[TR_RE_POS] ||
+                                  __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
+                                  __float_as_int(bm4) > st.run_val[TR_IM_NEG];
+                if (__any_sync(FULL, cand)) {
+                    const unsigned batch_off = (b_first + b) * PAPR_BATCH_SAMPLES;
+                    track_update<TR_PEAK, true, true, true>(st, r, bm0, batch_off, lane);
+                    track_update<TR_RE_POS, true, true, true>(st, r, bm1, batch_off, lane);
+                    track_update<TR_RE_NEG, true, true, true>(st, r, bm2, batch_off, lane);
+                    track_update<TR_IM_POS, true, true, true>(st, r, bm3, batch_off, lane);
+                    track_update<TR_IM_NEG, true, true, true>(st, r, bm4, batch_off, lane);
+                }
+            }
+
+            // ---- papr.c:104
+            if (nc == 1) {
+                double a0 = c0, a1 = c1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const double d = (double)v[j];
+                    a0 = __dadd_rn(a0, d);
+                    a1 = __dadd_rn(a1, d);
+                }
+                const unsigned b0 = __ballot_sync(FULL, xt_lsb(a0)), b1 = __ballot_sync(FULL, xt_lsb(a1));
+                const XtLink l = xt_link(b0, b1, lt);
+                const double i0 = __dsub_rn(a0, c0), i1 = __dsub_rn(a1, c1);
+                const unsigned p0 = (l.fixed ? l.base : P0) ^ l.flip, p1 = (l.fixed ? l.base : P1) ^ l.flip;
+                A0 = __dadd_rn(A0, p0 ? i1 : i0);
+                A1 = __dadd_rn(A1, p1 ? i1 : i0);
+                const XtLink e = xt_link(b0, b1, 0xffffffffu); // "lane 32": the parity the next batch is entered with
+                P0 = (e.fixed ? e.base : P0) ^ e.flip;
+                P1 = (e.fixed ? e.base : P1) ^ e.flip;
+            } else if (nc > 1) { // one run per candidate binade and per batch, for the chain to choose from
+                for (int cd = 0; cd < nc; ++cd) {
+                    const double d0 = xt_base(k_lo + cd, 0), d1 = xt_base(k_lo + cd, 1);
+                    double a0 = d0, a1 = d1;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double d = (double)v[j];
+                        a0 = __dadd_rn(a0, d);
+                        a1 = __dadd_rn(a1, d);
+                    }
+                    const unsigned b0 = __ballot_sync(FULL, xt_lsb(a0)), b1 = __ballot_sync(FULL, xt_lsb(a1));
+                    const XtLink l = xt_link(b0, b1, lt);
+                    const double i0 = __dsub_rn(a0, d0), i1 = __dsub_rn(a1, d1);
+                    const unsigned p0 = (l.fixed ? l.base : 0u) ^ l.flip, p1 = (l.fixed ? l.base : 1u) ^ l.flip;
+                    const double B0 = warp_sum_fixed(p0 ? i1 : i0), B1 = warp_sum_fixed(p1 ? i1 : i0);
+                    if (lane == 0) {
+                        PaprTileRun br;
+                        br.e0 = B0; br.e1 = B1;
+                        x.multi[((size_t)slot * XT_MAX_CAND + cd) * XT_TILE_BATCHES + b] = br;
+                        if (cd == 0) aux = __dadd_rn(aux, B0);
+                    }
+                }
+            } else if (!literal) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) aux = __dadd_rn(aux, (double)v[j]);
+            }
+        }
+
+        // ---- the tile's record
+        PaprTileRun tr;
+        int code;
+        if (nc == 1) {
+            tr.e0 = warp_sum_fixed(A0);
+            tr.e1 = warp_sum_fixed(A1);
+            code = (k_lo + XT_KBIAS) | (1 << 12);
+            if (lane == 0) wsum = __dadd_rn(wsum, tr.e0);
+        } else if (nc > 1) {
+            tr.e0 = aux; tr.e1 = 0.0;
+            code = (k_lo + XT_KBIAS) | (nc << 12) | (int)(slot << 16);
+            if (lane == 0) {
+                PaprTileRun z;
+                z.e0 = z.e1 = 0.0;
+                for (int cd = 0; cd < nc; ++cd)
+                    for (unsigned b = nb; b < XT_TILE_BATCHES; ++b)
+                        x.multi[((size_t)slot * XT_MAX_CAND + cd) * XT_TILE_BATCHES + b] = z;
+                wsum = __dadd_rn(wsum, aux);
+            }
+        } else if (literal) {
+            tr.e0 = tr.e1 = aux;
+            code = XT_CODE_LITERAL;
+            if (lane == 0) wsum = __dadd_rn(wsum, aux);
+        } else {
+            tr.e0 = warp_sum_fixed(aux); tr.e1 = 0.0;
+            code = 0;
+            if (lane == 0) wsum = __dadd_rn(wsum, tr.e0);
+        }
+        if (lane == 0) {
+            x.tile_run[x.tile_base + tile] = tr;
+            x.tile_code[x.tile_base + tile] = code;
+        }
+    }
+
+    // ---- CTA-level fold of the warps' states (fixed order), then into the CTA's persistent partial
+    {
+        __shared__ double s_wsum[PAPR_WARPS];
+        __shared__ int s_wval[PAPR_NTRACK][PAPR_WARPS];
+        __shared__ unsigned s_wpos[PAPR_NTRACK][PAPR_WARPS];
+        if (lane == 0) {
+            s_wsum[warp] = wsum;
+#pragma unroll
+            for (int t = 0; t < PAPR_NTRACK; ++t) {
+                const bool u = (st.upd >> t) & 1u;
+                s_wval[t][warp] = u ? st.run_val[t] : 0;
+                s_wpos[t][warp] = u ? st.run_pos[t] : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double xs = warp_sum_fixed(lane < PAPR_WARPS ? s_wsum[lane] : 0.0);
+            PaprCtaPartial *w = a.wp + blockIdx.x;
+            if (lane == 0) w->sum += xs;
+#pragma unroll
+            for (int t = 0; t < PAPR_NTRACK; ++t) {
+                int vv = lane < PAPR_WARPS ? s_wval[t][lane] : 0;
+                unsigned pos = lane < PAPR_WARPS ? s_wpos[t][lane] : 0xffffffffu;
+                const int vmax = __reduce_max_sync(FULL, vv);
+                const unsigned pmin = __reduce_min_sync(FULL, vv == vmax ? pos : 0xffffffffu);
+                if (lane == 0 && vmax > w->val[t]) {
+                    w->val[t] = vmax;
+                    w->idx[t] = a.first_index + pmin;
+                }
+            }
+        }
+    }
+    if (do_hist) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < st.ncells; i += PAPR_THREADS) {
+            unsigned c = s_hist[i + 1];
+            if (c) atomicAdd(&a.g_hist[i], (u64)c);
+        }
+        if (threadIdx.x == 0 && s_hist[st.ncells + 1]) atomicAdd(a.g_over, (u64)s_hist[st.ncells + 1]);
+    }
+}
+
+int papr_scan_tma_configure(void)
+{
+    return cudaFuncSetAttribute(papr_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM_BYTES) == cudaSuccess ? 0 : -1;
+}
+
+void papr_launch_scan_tma(const void *tmap, int grid, const PaprScanArgs &a, const PaprExactArgs &x, cudaStream_t s)
+{
+    papr_scan_tma_kernel<<<grid, PAPR_THREADS, XT_SMEM_BYTES, s>>>(*reinterpret_cast<const CUtensorMap *>(tmap), a, x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 32 tile runs -> one super-tile record (one warp per super-tile); multi tiles: 16 batch runs -> one tile
+// run per candidate binade
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ PaprTileRun xt_shfl_down(const PaprTileRun &r, int o)
+{
+    PaprTileRun n;
+    n.e0 = __shfl_down_sync(FULL, r.e0, o);
+    n.e1 = __shfl_down_sync(FULL, r.e1, o);
+    return n;
+}
+
+// ordered composition of the 32 lanes' runs (identity = {0, 0}); lane 0 holds the result
+__device__ __forceinline__ PaprTileRun xt_warp_compose(PaprTileRun r, int k)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) r = xt_compose(r, xt_shfl_down(r, o), k);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
+                                                              unsigned ntiles, const PaprTileRun *multi,
+                                                              PaprTileRun *multi_tile, PaprSuperRec *super)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
+    for (unsigned st = gw; st < nsuper; st += nw) {
+        const unsigned t = st * XT_SUPER_TILES + lane;
+        const bool have = t < ntiles;
+        const int code = have ? tile_code[t] : 0;
+        PaprTileRun run;
+        run.e0 = run.e1 = 0.0;
+        if (have) run = tile_run[t];
+        const int nc = have ? XT_CODE_NC(code) : 0, k = XT_CODE_K(code);
+        const double asum = run.e0;
+        if (nc > 1) {
+            const PaprTileRun *m = multi + (size_t)XT_CODE_SLOT(code) * XT_MAX_CAND * XT_TILE_BATCHES;
+            for (int cd = 0; cd < nc; ++cd) {
+                PaprTileRun r = m[cd * XT_TILE_BATCHES];
+                for (int b = 1; b < XT_TILE_BATCHES; ++b) r = xt_compose(r, m[cd * XT_TILE_BATCHES + b], k + cd);
+                multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + cd] = r;
+            }
+        }
+        const unsigned real = __ballot_sync(FULL, have);
+        const int kk = __shfl_sync(FULL, k, __ffs(real) - 1);
+        const bool simple = __all_sync(FULL, !have || (nc == 1 && k == kk)) && real != 0;
+        if (!simple) run.e0 = run.e1 = 0.0;
+        const PaprTileRun total = xt_warp_compose(run, kk);
+        const double at = warp_sum_fixed(asum);
+        if (lane == 0) {
+            PaprSuperRec s;
+            s.e0 = total.e0; s.e1 = total.e1; s.asum = at;
+            s.code = simple ? kk + XT_KBIAS : (real ? XT_SUPER_COMPLEX : XT_SUPER_EMPTY);
+            s.pad = 0;
+            super[st] = s;
+        }
+    }
+}
+
+void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi,
+                            PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s)
+{
+    papr_xt_compose_kernel<<<grid, 256, 0, s>>>(tile_run, tile_code, ntiles, multi, multi_tile, super);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the chain: one CTA of 1024 threads
+// ------------------------------------------------------------------------------------------------
+enum { // PaprChainList.why
+    XW_NONE = 0, XW_TOO_MANY_CROSSINGS = 1, XW_SUPER_MISPREDICTED = 2, XW_TILE_NO_CANDIDATE = 3, XW_TWO_CROSSINGS_IN_TILE = 4,
+    XW_BATCH_NOT_FOUND = 5, XW_LANE_NOT_FOUND = 6, XW_TOO_MANY_ITEMS = 7, XW_WALK_BINADE = 8, XW_WALK_OVERFLOW = 9,
+    XW_WALK_LITERAL = 10, XW_WALK_ABS = 11, XW_START_UNKNOWN = 12,
+};
+
+struct XtCtx {
+    const PaprSuperRec *super;
+    const PaprTileRun *tile_run;
+    const int *tile_code;
+    const PaprTileRun *multi, *multi_tile;
+    unsigned ntiles, nsuper;
+    const float *iq;               // the shard (for the 8 + 248 samples around each crossing)
+    unsigned long long nsamples;
+};
+
+// the run of tile t under binade k; false if the tile offers no such candidate
+__device__ __forceinline__ bool xt_tile_rec(const XtCtx &c, unsigned t, int k, PaprTileRun *out)
+{
+    out->e0 = out->e1 = 0.0;
+    if (t >= c.ntiles) return true;
+    const int code = c.tile_code[t], nc = XT_CODE_NC(code), K = XT_CODE_K(code);
+    if (nc == 1 && K == k) { *out = c.tile_run[t]; return true; }
+    if (nc > 1 && k >= K && k < K + nc) { *out = c.multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (k - K)]; return true; }
+    // an all-zero tile is the identity in any binade
+    if (!(code & XT_CODE_LITERAL) && c.tile_run[t].e0 == 0.0) return true;
+    return false;
+}
+
+__device__ __forceinline__ double xt_warp_excl_scan(double v, int lane, double *total)
+{
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += u;
+    }
+    *total = __shfl_sync(FULL, inc, 31);
+    return inc - v; // exclusive (approximate sums only)
+}
+
+struct XtItemKey { unsigned long long pos; }; // shard-local sample index at which the item starts (sort key)
+
+// thread 0 of the CTA: apply the items in order.  Returns the status.
+__device__ int xt_walk(const PaprChainItem *item, int n, double *state, int *why)
+{
+    double s = *state;
+    for (int i = 0; i < n; ++i) {
+        const PaprChainItem &it = item[i];
+        if (it.type == XT_IT_SEG) {
+            if (it.d[0] == 0.0 && it.d[1] == 0.0) continue; // nothing but zeros: the identity in any binade
+            if (xt_expo(s) != it.k) { *why = XW_WALK_BINADE; return XT_FALLBACK; }
+            const double inc = xt_lsb(s) ? it.d[1] : it.d[0];
+            const double s2 = __dadd_rn(s, inc); // whole ulps on both sides: exact while it stays in the binade
+            if (!(inc >= 0.0) || !(s2 < xt_base(it.k + 1, 0))) { *why = XW_WALK_OVERFLOW; return XT_FALLBACK; }
+            s = s2;
+        } else if (it.type == XT_IT_LIT) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, it.d[j]); // papr.c:104 as written
+            if (xt_expo(s) != it.k) { *why = XW_WALK_LITERAL; return XT_FALLBACK; }
+        } else {
+            if (s != 0.0) { *why = XW_WALK_ABS; return XT_FALLBACK; }
+            s = it.d[0];
+        }
+    }
+    *state = s;
+    return XT_OK;
+}
+
+#define XT_CHAIN_T 1024
+#define XT_MAX_XTILES 64
+
+// Builds the item list of this shard: out->item[0..n) in file order.  pre_approx = approximate running sum
+// before the shard (0 for the first); literal tiles produce an ABS item.
+__device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList *out)
+{
+    __shared__ double s_scan[XT_CHAIN_T];
+    __shared__ PaprTileRun s_piece[XT_CHAIN_T + XT_MAX_CROSS + 1];
+    __shared__ short s_piece_k[XT_CHAIN_T + XT_MAX_CROSS + 1]; // the binade each piece was composed for
+    __shared__ unsigned s_xs[XT_MAX_CROSS];    // crossing super-tiles, ascending
+    __shared__ double s_xp[XT_MAX_CROSS];      // approximate running sum at their start
+    __shared__ unsigned s_xt[XT_MAX_XTILES];   // crossing tiles
+    __shared__ double s_xtp[XT_MAX_XTILES];
+    __shared__ unsigned long long s_key[XT_MAX_ITEMS];
+    __shared__ int s_nx, s_nxt, s_nitems, s_status, s_why;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    PaprChainItem *stage = out->item; // staged unsorted in place? no: sorted copy needs a second buffer -> see below
+    if (t == 0) { s_nx = 0; s_nxt = 0; s_nitems = 0; s_status = XT_OK; s_why = XW_NONE; }
+    __syncthreads();
+    auto fail = [&](int why) { if (atomicCAS(&s_status, XT_OK, XT_FALLBACK) == XT_OK) s_why = why; };
+    // item staging area: the second half of out->item is not needed until the sort, so items are staged in a
+    // separate global scratch that follows the list (the caller allocates two lists back to back)
+    PaprChainItem *scratch = (out + 1)->item;
+    auto emit = [&](int type, int k, unsigned long long pos, const double *d, int nd) {
+        const int i = atomicAdd(&s_nitems, 1);
+        if (i >= XT_MAX_ITEMS) { fail(XW_TOO_MANY_ITEMS); return; }
+        scratch[i].type = type;
+        scratch[i].k = k;
+        for (int j = 0; j < 8; ++j) scratch[i].d[j] = j < nd ? d[j] : 0.0;
+        s_key[i] = pos;
+    };
+
+    // ---- 1. approximate running sum at every super-tile (block scan of chunk sums)
+    const unsigned m = (c.nsuper + XT_CHAIN_T - 1) / XT_CHAIN_T;
+    const unsigned lo = min(c.nsuper, (unsigned)t * m), hi = min(c.nsuper, lo + m);
+    double chunk = 0.0;
+    for (unsigned i = lo; i < hi; ++i) chunk += c.super[i].asum;
+    s_scan[t] = chunk;
+    __syncthreads();
+    for (int o = 1; o < XT_CHAIN_T; o <<= 1) {
+        const double u = t >= o ? s_scan[t - o] : 0.0;
+        __syncthreads();
+        s_scan[t] += u;
+        __syncthreads();
+    }
+    const double total = pre_approx + s_scan[XT_CHAIN_T - 1];
+    if (t == 0) out->approx = s_scan[XT_CHAIN_T - 1];
+    if (!isfinite(total)) { // NaN / Inf among the powers: so is the reference's sum, nothing to emulate
+        if (t == 0) { out->n = 0; out->status = XT_NONFINITE; out->why = XW_NONE; }
+        __syncthreads();
+        return;
+    }
+    const double p_chunk = pre_approx + (s_scan[t] - chunk);
+
+    // ---- 2. super-tiles inside which the running sum changes binade (or starts from zero)
+    {
+        double p = p_chunk;
+        for (unsigned i = lo; i < hi; ++i) {
+            const double pn = p + c.super[i].asum;
+            if (xt_expo(p) != xt_expo(pn)) {
+                const int j = atomicAdd(&s_nx, 1);
+                if (j < XT_MAX_CROSS) { s_xs[j] = i; s_xp[j] = p; } else fail(XW_TOO_MANY_CROSSINGS);
+            }
+            p = pn;
+        }
+    }
+    __syncthreads();
+    const int nx = min(s_nx, XT_MAX_CROSS);
+    if (t == 0) // ascending (<= 48 entries)
+        for (int i = 1; i < nx; ++i) {
+            const unsigned v = s_xs[i];
+            const double pv = s_xp[i];
+            int j = i - 1;
+            while (j >= 0 && s_xs[j] > v) { s_xs[j + 1] = s_xs[j]; s_xp[j + 1] = s_xp[j]; --j; }
+            s_xs[j + 1] = v; s_xp[j + 1] = pv;
+        }
+    __syncthreads();
+
+    // ---- 3. the stretches of super-tiles between them: every thread composes its chunk, cut at the crossing
+    //         super-tiles; piece index t + (crossings before it) puts all pieces in file order, and the pieces
+    //         of stretch number s are exactly those with index - thread == s
+    {
+        int xb = 0; // crossing super-tiles before this chunk
+        while (xb < nx && s_xs[xb] < lo) ++xb;
+        int seg = xb;
+        double p = p_chunk;
+        PaprTileRun cur;
+        cur.e0 = cur.e1 = 0.0;
+        int k = xt_expo(p);
+        for (unsigned i = lo; i < hi; ++i) {
+            const PaprSuperRec sr = c.super[i];
+            if (seg < nx && s_xs[seg] == i) {
+                s_piece[t + seg] = cur;
+                s_piece_k[t + seg] = (short)k;
+                cur.e0 = cur.e1 = 0.0;
+                ++seg;
+                p += sr.asum;
+                k = xt_expo(p);
+                continue;
+            }
+            if (sr.code == k + XT_KBIAS) {
+                PaprTileRun r;
+                r.e0 = sr.e0; r.e1 = sr.e1;
+                cur = xt_compose(cur, r, k);
+            } else if (sr.code == XT_SUPER_COMPLEX) {
+                for (unsigned tt = 0; tt < XT_SUPER_TILES; ++tt) {
+                    PaprTileRun r;
+                    if (!xt_tile_rec(c, i * XT_SUPER_TILES + tt, k, &r)) { fail(XW_TILE_NO_CANDIDATE); break; }
+                    cur = xt_compose(cur, r, k);
+                }
+            } else if (sr.code != XT_SUPER_EMPTY && !(sr.asum == 0.0)) {
+                fail(XW_SUPER_MISPREDICTED);
+            }
+            p += sr.asum;
+        }
+        s_piece[t + seg] = cur;
+        s_piece_k[t + seg] = (short)k;
+    }
+    __syncthreads();
+    for (int s = warp; s <= nx; s += XT_CHAIN_T / 32) { // one warp per stretch
+        const unsigned a = s == 0 ? 0u : s_xs[s - 1] + 1u, b = s == nx ? c.nsuper : s_xs[s];
+        if (a >= b) continue;
+        // binade of the stretch: the running sum at its start
+        double p0;
+        if (s == 0) p0 = pre_approx;
+        else p0 = s_xp[s - 1] + c.super[s_xs[s - 1]].asum;
+        const int k = xt_expo(p0);
+        const unsigned ta = a / m, tb = (b - 1) / m;
+        // lanes take contiguous thread ranges
+        const unsigned cnt = tb - ta + 1, per = (cnt + 31) / 32;
+        PaprTileRun r;
+        r.e0 = r.e1 = 0.0;
+        for (unsigned q = 0; q < per; ++q) {
+            const unsigned th = ta + lane * per + q;
+            if (th <= tb) {
+                const PaprTileRun pc = s_piece[th + s];
+                // a piece composed for another binade (the approximate running sum read differently by two
+                // threads right at a power of two) must not be mixed in
+                if (s_piece_k[th + s] != (short)k && !(pc.e0 == 0.0 && pc.e1 == 0.0)) fail(XW_SUPER_MISPREDICTED);
+                r = xt_compose(r, pc, k);
+            }
+        }
+        r = xt_warp_compose(r, k);
+        if (lane == 0) {
+            const double d[2] = {r.e0, r.e1};
+            emit(XT_IT_SEG, k, (unsigned long long)a * XT_SUPER_SAMPLES, d, 2);
+        }
+    }
+
+    // ---- 4. inside every crossing super-tile: the tiles in which it happens, and the stretches of tiles between
+    for (int x = warp; x < nx; x += XT_CHAIN_T / 32) {
+        const unsigned st = s_xs[x], tl = st * XT_SUPER_TILES + lane;
+        const bool have = tl < c.ntiles;
+        const int code = have ? c.tile_code[tl] : 0;
+        const double asum = have ? c.tile_run[tl].e0 : 0.0;
+        double tot;
+        const double pl = s_xp[x] + xt_warp_excl_scan(asum, lane, &tot), pa = pl + asum;
+        const bool lit = have && (code & XT_CODE_LITERAL);
+        const bool cross = have && !lit && xt_expo(pl) != xt_expo(pa);
+        if (cross && xt_expo(pa) != xt_expo(pl) + 1) fail(xt_expo(pl) <= -4000 ? XW_START_UNKNOWN : XW_TWO_CROSSINGS_IN_TILE);
+        if (lit) {
+            if (pl != 0.0) fail(XW_WALK_ABS);
+            const double d[1] = {c.tile_run[tl].e0};
+            emit(XT_IT_ABS, 0, (unsigned long long)tl * XT_TILE_SAMPLES, d, 1);
+        }
+        if (cross) {
+            const int j = atomicAdd(&s_nxt, 1);
+            if (j < XT_MAX_XTILES) { s_xt[j] = tl; s_xtp[j] = pl; } else fail(XW_TOO_MANY_CROSSINGS);
+        }
+        // stretches of ordinary tiles between the boundaries (crossing / literal tiles)
+        unsigned bnd = __ballot_sync(FULL, cross || lit);
+        int a = 0;
+        while (a < 32) {
+            const unsigned rest = bnd >> a;
+            const int b = rest ? a + (__ffs(rest) - 1) : 32; // stretch = lanes [a, b)
+            if (b > a) {
+                // binade at its start
+                const double pst = __shfl_sync(FULL, pl, a);
+                const int k = xt_expo(pst);
+                PaprTileRun r;
+                r.e0 = r.e1 = 0.0;
+                bool ok = true;
+                if (lane >= a && lane < b) ok = xt_tile_rec(c, tl, k, &r);
+                if (!__all_sync(FULL, ok)) { if (lane == 0) fail(XW_TILE_NO_CANDIDATE); }
+                r = xt_warp_compose(r, k);
+                if (lane == 0) {
+                    const double d[2] = {r.e0, r.e1};
+                    emit(XT_IT_SEG, k, (unsigned long long)(st * XT_SUPER_TILES + a) * XT_TILE_SAMPLES, d, 2);
+                }
+            }
+            a = b + 1;
+        }
+    }
+    __syncthreads();
+
+    // ---- 5. inside every crossing tile: the batch, then the 8 samples
+    const int nxt = min(s_nxt, XT_MAX_XTILES);
+    for (int x = warp; x < nxt; x += XT_CHAIN_T / 32) {
+        const unsigned tl = s_xt[x];
+        const int code = c.tile_code[tl], nc = XT_CODE_NC(code), K = XT_CODE_K(code);
+        const int kb = xt_expo(s_xtp[x]), ka = kb + 1;
+        if (nc < 2 || kb < K || ka >= K + nc) { if (lane == 0) fail(XW_TILE_NO_CANDIDATE); continue; }
+        const PaprTileRun *mb = c.multi + ((size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (kb - K)) * XT_TILE_BATCHES;
+        const PaprTileRun *ma = mb + XT_TILE_BATCHES;
+        PaprTileRun rb, ra;
+        rb.e0 = rb.e1 = ra.e0 = ra.e1 = 0.0;
+        if (lane < XT_TILE_BATCHES) { rb = mb[lane]; ra = ma[lane]; }
+        double tot;
+        const double pl = s_xtp[x] + xt_warp_excl_scan(rb.e0, lane, &tot);
+        const unsigned xb = __ballot_sync(FULL, lane < XT_TILE_BATCHES && xt_expo(pl) != xt_expo(pl + rb.e0));
+        if (__popc(xb) != 1) { if (lane == 0) fail(XW_BATCH_NOT_FOUND); continue; }
+        const int bx = __ffs(xb) - 1;
+        const double pbx = __shfl_sync(FULL, pl, bx);
+        const unsigned long long tile_pos = (unsigned long long)tl * XT_TILE_SAMPLES;
+        { // batches before: binade kb; after: ka
+            PaprTileRun r = rb;
+            if (lane >= bx) r.e0 = r.e1 = 0.0;
+            r = xt_warp_compose(r, kb);
+            PaprTileRun q = ra;
+            if (lane <= bx || lane >= XT_TILE_BATCHES) q.e0 = q.e1 = 0.0;
+            q = xt_warp_compose(q, ka);
+            if (lane == 0) {
+                const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
+                emit(XT_IT_SEG, kb, tile_pos + 1, d, 2);                                  // after the tile-level stretch that ends here
+                emit(XT_IT_SEG, ka, tile_pos + (unsigned long long)(bx + 1) * PAPR_BATCH_SAMPLES, e, 2);
+            }
+        }
+        // the crossing batch: this lane's 8 samples, runs for both binades
+        const unsigned long long s0 = tile_pos + (unsigned long long)bx * PAPR_BATCH_SAMPLES + 8ull * lane;
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = 0.0;
+            if (s0 + j < c.nsamples) {
+                const float2 h = *reinterpret_cast<const float2 *>(c.iq + 2 * (s0 + j));
+                v[j] = (double)power_of(h.x, h.y);
+            }
+        }
+        PaprTileRun lb, la;
+        {
+            double a0 = xt_base(kb, 0), a1 = xt_base(kb, 1), b0 = xt_base(ka, 0), b1 = xt_base(ka, 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a0 = __dadd_rn(a0, v[j]); a1 = __dadd_rn(a1, v[j]);
+                b0 = __dadd_rn(b0, v[j]); b1 = __dadd_rn(b1, v[j]);
+            }
+            lb.e0 = __dsub_rn(a0, xt_base(kb, 0)); lb.e1 = __dsub_rn(a1, xt_base(kb, 1));
+            la.e0 = __dsub_rn(b0, xt_base(ka, 0)); la.e1 = __dsub_rn(b1, xt_base(ka, 1));
+        }
+        const double ql = pbx + xt_warp_excl_scan(lb.e0, lane, &tot);
+        const unsigned xl = __ballot_sync(FULL, xt_expo(ql) != xt_expo(ql + lb.e0));
+        if (__popc(xl) != 1) { if (lane == 0) fail(XW_LANE_NOT_FOUND); continue; }
+        const int lx = __ffs(xl) - 1;
+        {
+            PaprTileRun r = lb;
+            if (lane >= lx) r.e0 = r.e1 = 0.0;
+            r = xt_warp_compose(r, kb);
+            PaprTileRun q = la;
+            if (lane <= lx) q.e0 = q.e1 = 0.0;
+            q = xt_warp_compose(q, ka);
+            const unsigned long long bpos = tile_pos + (unsigned long long)bx * PAPR_BATCH_SAMPLES;
+            if (lane == 0) {
+                const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
+                emit(XT_IT_SEG, kb, bpos + 2, d, 2);
+                emit(XT_IT_SEG, ka, bpos + 8ull * (lx + 1), e, 2);
+            }
+            if (lane == lx) emit(XT_IT_LIT, ka, bpos + 8ull * lx + 3, v, 8);
+        }
+    }
+    __syncthreads();
+
+    // ---- 6. file order: rank every item by its key, scatter into the list
+    const int ni = min(s_nitems, XT_MAX_ITEMS);
+    for (int i = t; i < ni; i += XT_CHAIN_T) {
+        const unsigned long long ki = s_key[i];
+        int rank = 0;
+        for (int j = 0; j < ni; ++j) rank += (s_key[j] < ki) || (s_key[j] == ki && j < i);
+        out->item[rank] = scratch[i];
+    }
+    if (t == 0) { out->n = ni; out->status = s_status; out->why = s_why; }
+    __threadfence();
+    __syncthreads();
+}
+
+// single shard: prepare + walk
+__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_kernel(XtCtx c, PaprChainList *out)
+{
+    xt_chain_prepare(c, 0.0, out);
+    if (threadIdx.x == 0 && out->status == XT_OK) {
+        double s = 0.0;
+        int why = XW_NONE;
+        out->status = xt_walk(out->item, out->n, &s, &why);
+        out->why = why;
+        out->exact = s;
+    }
+}
+
+void papr_launch_xt_chain(const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
+                          const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
+                          PaprChainList *out, cudaStream_t s)
+{
+    XtCtx c;
+    c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
+    c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
+    papr_xt_chain_kernel<<<1, XT_CHAIN_T, 0, s>>>(c, out);
+}

@@ -19,178 +19,7 @@
 //     threshold (or, in the fused mode, may contain it) are additionally counted exactly, one counter
 //     per float32 value, in a small L2-resident fine table.  level_count[j] = samples in cells above
 //     the threshold's cell + the fine counters above the threshold inside its cell.  Exact.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stddef.h>
-#include <stdint.h>
-
-#include "papr_device.cuh"
-
-#define FULL 0xffffffffu
-typedef unsigned long long u64;
-
-// ------------------------------------------------------------------------------------------------
-// small helpers
-// ------------------------------------------------------------------------------------------------
-// 16-byte streaming load: read-only path, do not allocate in L1 (every byte is used exactly once)
-__device__ __forceinline__ float4 ldg_stream(const float4 *p)
-{
-    float4 r;
-    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-        : "l"(p));
-    return r;
-}
-
-// papr.c:103 — (I*I)+(Q*Q) with each operation rounded to float32 (the canonical x86-64 build of
-// the reference emits mulss, mulss, addss; an FMA here changes the printed percentages)
-__device__ __forceinline__ float power_of(float i, float q)
-{
-    return __fadd_rn(__fmul_rn(i, i), __fmul_rn(q, q));
-}
-
-template <int T>
-__device__ __forceinline__ void track_vals(const float4 &q, float v0, float v1, float &a, float &b)
-{
-    if (T == TR_PEAK) { a = v0; b = v1; }
-    if (T == TR_RE_POS) { a = q.x; b = q.z; }
-    if (T == TR_RE_NEG) { a = -q.x; b = -q.z; }
-    if (T == TR_IM_POS) { a = q.y; b = q.w; }
-    if (T == TR_IM_NEG) { a = -q.y; b = -q.w; }
-}
-
-__device__ __forceinline__ double warp_sum_fixed(double x)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
-    return x; // lane 0 holds the total; same association order every run
-}
-
-// (value desc, index asc): lower index wins ties = the reference's strict compare in file order
-__device__ __forceinline__ bool better(int va, u64 ia, int vb, u64 ib)
-{
-    return va > vb || (va == vb && ia < ib);
-}
-
-// ------------------------------------------------------------------------------------------------
-// the scan kernel: pass 1 (STATS), pass 2 (HIST) or both in one sweep over the shard
-// ------------------------------------------------------------------------------------------------
-// dynamic shared memory of the scan kernel: u32 hist[NCELLS_MAX+2] | u32 fine_base[NCELLS_MAX+2]
-// slot 0 = below the planned range, slots 1..ncells = cells, slot ncells+1 = above the range
-extern __shared__ __align__(16) unsigned char scan_smem[];
-#define SCAN_SMEM_BYTES (8 * (PAPR_NCELLS_MAX + 2))
-
-template <bool STATS, bool HIST>
-struct ScanState {
-    // pass 1
-    double dsum;
-    int run_val[PAPR_NTRACK];
-    unsigned run_pos[PAPR_NTRACK]; // sample offset inside this launch of the current first occurrence
-    unsigned upd;
-    // pass 2
-    u64 *g_fine;
-    unsigned smem_slot1; // shared-window byte address of slot 1 (= cell 0)
-    int sh, cell_base, ncells;
-    unsigned fmask;
-};
-
-// The CCDF pass, per sample.  No divergence up to the (warp-level infrequent) fine-table update:
-// the cell index is clamped into [0, ncells+1] where slot 0 collects everything below the planned
-// range (63 % of a Gaussian-like capture) and slot ncells+1 everything above it; every lane issues the
-// shared-memory increment (ATOMS.POPC.INC merges lanes that hit the same word, so the crowded slot 0
-// costs one update per warp) and reads the slot's fine-table base (0 = no threshold can lie here).
-template <bool STATS, bool HIST>
-__device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, unsigned bits)
-{
-    // shared-window byte address of the sample's slot
-    int d = (int)(bits >> st.sh) - st.cell_base;
-    // a NaN power exceeds no level (`value > level[j]` is false, papr.c:148); only the stand-alone CCDF
-    // pass can meet one with levels to count against - with the statistics in the same sweep the sum is
-    // NaN too and the reference prints no levels at all
-    if (!STATS) d = bits > 0x7f800000u ? -1 : d;
-    d = max(min(d, st.ncells), -1);
-    return st.smem_slot1 + ((unsigned)d << 2);
-}
-
-__device__ __forceinline__ unsigned hist_bump(unsigned addr)
-{
-    unsigned fb;
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(fb) : "r"(addr), "n"(4 * (PAPR_NCELLS_MAX + 2)));
-    return fb;
-}
-
-// the two samples of one 16-byte load
-template <bool STATS, bool HIST>
-__device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, float v1)
-{
-    const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
-    const unsigned f0 = hist_bump(hist_slot(st, b0));
-    const unsigned f1 = hist_bump(hist_slot(st, b1));
-    if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
-        if (f0) atomicAdd(&st.g_fine[f0 - 1u + (b0 & st.fmask)], 1ull);
-        if (f1) atomicAdd(&st.g_fine[f1 - 1u + (b1 & st.fmask)], 1ull);
-    }
-}
-
-template <int T, bool STATS, bool HIST>
-__device__ __forceinline__ void track_update(ScanState<STATS, HIST> &st, const float4 (&r)[PAPR_U],
-                                             float bm, unsigned batch_off, int lane)
-{
-    int w = __reduce_max_sync(FULL, __float_as_int(bm));
-    if (w > st.run_val[T]) { // warp-uniform and rare: locate the first sample of the batch equal to w
-        unsigned pos = 0xffffffffu;
-#pragma unroll
-        for (int u = PAPR_U - 1; u >= 0; --u) {
-            float v0 = power_of(r[u].x, r[u].y), v1 = power_of(r[u].z, r[u].w), a, b;
-            track_vals<T>(r[u], v0, v1, a, b);
-            unsigned p = 2u * (unsigned)(u * 32 + lane);
-            if (__float_as_int(b) == w) pos = p + 1;
-            if (__float_as_int(a) == w) pos = p;
-        }
-        pos = __reduce_min_sync(FULL, pos);
-        st.run_val[T] = w;
-        st.run_pos[T] = batch_off + pos;
-        st.upd |= 1u << T;
-    }
-}
-
-template <bool STATS, bool HIST>
-__device__ __forceinline__ void process_batch(ScanState<STATS, HIST> &st, const float4 (&r)[PAPR_U],
-                                              unsigned batch_off, int lane)
-{
-    float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
-#pragma unroll
-    for (int u = 0; u < PAPR_U; ++u) {
-        const float4 q = r[u];
-        float v0 = power_of(q.x, q.y);
-        float v1 = power_of(q.z, q.w);
-        if (STATS) {
-            st.dsum += (double)v0; // papr.c:104 (order differs from the file order)
-            st.dsum += (double)v1;
-            // fmaxf drops NaN operands, like the reference's comparisons (papr.c:105-126)
-            bm0 = fmaxf(bm0, fmaxf(v0, v1));
-            bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
-            bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
-            bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
-            bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
-        }
-        if (HIST) hist_pair(st, v0, v1);
-    }
-    if (STATS) {
-        // warp-uniform and rare after the first few batches: does any lane beat a running maximum?
-        const bool cand = __float_as_int(bm0) > st.run_val[TR_PEAK] || __float_as_int(bm1) > st.run_val[TR_RE_POS] ||
-                          __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
-                          __float_as_int(bm4) > st.run_val[TR_IM_NEG];
-        if (__any_sync(FULL, cand)) {
-            track_update<TR_PEAK>(st, r, bm0, batch_off, lane);
-            track_update<TR_RE_POS>(st, r, bm1, batch_off, lane);
-            track_update<TR_RE_NEG>(st, r, bm2, batch_off, lane);
-            track_update<TR_IM_POS>(st, r, bm3, batch_off, lane);
-            track_update<TR_IM_NEG>(st, r, bm4, batch_off, lane);
-        }
-    }
-}
+#include "papr_scan_common.cuh"
 
 template <bool STATS, bool HIST>
 __global__ void __launch_bounds__(PAPR_THREADS, PAPR_CTAS_PER_SM) papr_scan_kernel(const PaprScanArgs a)
@@ -421,9 +250,16 @@ __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const Pa
 __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
                                                                    PaprDevStats *out, bool with_levels,
                                                                    PaprTables tb, int graph, PaprDevStats *merged,
-                                                                   PaprDevLevels *lv, u64 *status_word)
+                                                                   PaprDevLevels *lv, u64 *status_word,
+                                                                   const PaprChainList *chain, int *chain_report)
 {
     reduce_partials(wp, nctas, n, out);
+    if (chain && threadIdx.x == 0) { // the sequential sum chained on the device replaces the approximate one
+        const int st = chain->status;
+        if (st == XT_OK) out->sum = chain->exact;
+        chain_report[0] = st;
+        chain_report[1] = chain->why;
+    }
     if (!with_levels) return;
     __syncthreads(); // thread 0's global writes are read back by thread 0 only
     merge_and_levels(out, 1, tb, graph, merged, lv, status_word);
@@ -432,14 +268,15 @@ __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprCt
 void papr_launch_stats_finalize(const PaprCtaPartial *wp, int nctas, u64 n, PaprDevStats *out, cudaStream_t s)
 {
     PaprTables none = {nullptr, nullptr, 0};
-    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, out, false, none, 0, nullptr, nullptr, nullptr);
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, out, false, none, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
                                  PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
-                                 u64 *status_word, cudaStream_t s)
+                                 u64 *status_word, const PaprChainList *chain, int *chain_report, cudaStream_t s)
 {
-    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, true, t, graph, merged, lv, status_word);
+    papr_stats_finalize_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, true, t, graph, merged, lv, status_word, chain,
+                                                   chain_report);
 }
 
 __global__ void __launch_bounds__(FIN_T) papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb,
@@ -608,7 +445,7 @@ __device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, flo
     const double s1 = pre[0], s2 = pre[1], cnt = pre[2];
     PaprPlan pl;
     pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
-    pl.levels_covered = 0; pl.window = 0.f; pl.pad = xchg_timeout; pl.avg_pred = 0.0;
+    pl.levels_covered = 0; pl.window = 0.f; pl.pad = xchg_timeout; pl.avg_pred = 0.0; pl.wcv = 0.0;
     const bool ok = cnt >= 16.0 && s1 > 0.0 && isfinite(s1) && isfinite(s2);
     if (!ok) { // nothing to predict from: the exact pass will run
         for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) fine_base[c] = 0;
@@ -650,6 +487,7 @@ __device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, flo
     if (t == 0) {
         pl.sh = sh; pl.cell_base = base; pl.ncells = ncells; pl.n_amb = n_amb; pl.status = PLAN_HIST;
         pl.levels_covered = cov; pl.window = (float)w; pl.avg_pred = avg;
+        pl.wcv = (double)sigmas * sqrt(var_b) / mean_b;
         *plan = pl;
     }
 }
@@ -686,7 +524,7 @@ __global__ void __launch_bounds__(1024) papr_plan_exact_kernel(const PaprDevLeve
     const int L = lv->L;
     PaprPlan pl;
     pl.sh = PAPR_SH_MIN; pl.cell_base = 0; pl.ncells = 0; pl.n_amb = 0; pl.status = 0;
-    pl.levels_covered = L; pl.window = 0.f; pl.pad = 0; pl.avg_pred = lv->avg;
+    pl.levels_covered = L; pl.window = 0.f; pl.pad = 0; pl.avg_pred = lv->avg; pl.wcv = 0.0;
     if (L <= 0) {
         for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) fine_base[c] = 0;
         if (t == 0) *plan = pl;

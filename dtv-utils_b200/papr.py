@@ -41,7 +41,7 @@ class PaprResult(C.Structure):
                 ("nlevels", C.c_int32), ("level", C.c_float * MAX_LEVELS),
                 ("level_count", C.c_int64 * MAX_LEVELS), ("mode_used", C.c_int32), ("fused_miss", C.c_int32),
                 ("device_ms", C.c_float), ("scan_ms", C.c_float), ("kernel_launches", C.c_uint32),
-                ("reserved", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("sum_path", C.c_uint32), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
     def counts(self):
         return [self.level_count[j] for j in range(self.nlevels)]

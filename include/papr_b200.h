@@ -76,7 +76,10 @@ typedef struct papr_result {
     float    device_ms;                    /* GPU time of the analysis (CUDA events on the engine stream) */
     float    scan_ms;                      /* GPU time of the dominant scan kernel launch(es) */
     uint32_t kernel_launches;              /* kernels launched for this analysis */
-    uint32_t reserved;
+    uint32_t sum_path;                     /* how stats.sum was obtained: 0 = any fixed order (exact_sum off, or NaN/Inf
+                                              powers: nothing to emulate); 1 = papr.c:104 emulated inside the fused sweep and
+                                              chained on the device; 2 = two-sweep emulation (bits 8-15: why the device chain
+                                              declined, 0 if it was not tried); 3 = emulated chunk by chunk while streaming in */
     uint64_t h2d_bytes, d2h_bytes;         /* bytes moved across PCIe by this call */
 } papr_result;
 
@@ -94,9 +97,10 @@ void *papr_engine_stream(papr_engine *e);
  * "fused_min_samples", "fine_bytes_log2", "predict_bias" (test hook: scales the fused mode's predicted
  * mean; anything but 1.0 provokes the a-posteriori miss and the exact redo), "max_resident_bytes": host-side captures larger than this
  * (default 0 = what the GPU has free, less 1 GiB) are not kept resident in HBM but streamed twice,
- * like the reference reads its file twice (papr.c:142); "exact_sum": -1 (default) = emulate the reference's sequential
- * double sum (papr.c:104) bit for bit on the file/host path only, 0 = never, 1 = also on the
- * device-resident path).  Returns PAPR_ERR_ARG for an unknown name. */
+ * like the reference reads its file twice (papr.c:142); "exact_sum": != 0 (default) = emulate the reference's sequential
+ * double sum (papr.c:104) bit for bit on every path - inside the fused sweep for large device-resident shards
+ * (papr_result.sum_path says which way), 0 = any fixed summation order; "xchg_timeout_s": how long the in-kernel
+ * peer exchange waits for a rank before ALL ranks give up (default 30)).  Returns PAPR_ERR_ARG for an unknown name. */
 int  papr_engine_set(papr_engine *e, const char *name, double value);
 
 /* ---- the process boundary: replaces main(), papr.c:32-196 ------------------------------------ */

@@ -398,3 +398,65 @@ def test_ofdm_producer_capture_against_oracle(built, eng, torch_cuda):
             assert built.format_result(eng.analyze_device(d, n, graph)) == want
         eng.set("mode", 0)
         assert built.format_result(eng.analyze_host(host, graph=graph)) == want
+
+
+# ---- the sequential sum INSIDE the fused sweep (papr_exact.cu): TMA-fed scan + device chain ----------
+def _bits(x):
+    import struct
+    return struct.pack("<d", x)
+
+
+@pytest.mark.parametrize("n", [8192 + 5, (1 << 17) + 255, (1 << 20) + 16 * 7 + 3, (1 << 22) + 4096 * 3 + 256 * 5 + 8,
+                               (1 << 24) + 1])
+def test_sum_chained_inside_the_sweep_equals_sequential_sum(built, eng, torch_cuda, n):
+    """Default resident path, fused mode: stats.sum must be the reference's sequential double sum bit for
+    bit AND must have been produced by the device chain (sum_path == 1), for captures whose length is not
+    a multiple of the 16-sample TMA row, the 256-sample batch or the 4096-sample tile."""
+    for seed, scale in ((31, 1.0), (32, 37.5), (33, 1e-9)):
+        f = (fixtures.siggen(0, n, seed) * np.float32(scale)).astype(np.float32)
+        st, *_ = oracle_binding.analyze(f, False)
+        d = _dev(torch_cuda, f)
+        eng.set("mode", 2)
+        try:
+            for graph in (False, True):
+                res = eng.analyze_device(d, n, graph)
+                assert res.sum_path & 0xff == 1, (n, seed, "device chain declined, why=%d" % (res.sum_path >> 8))
+                assert _bits(res.stats.sum) == _bits(st.sum), (n, seed)
+                assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), graph)
+        finally:
+            eng.set("mode", 0)
+
+
+def test_sum_chain_declines_rather_than_guessing(built, eng, torch_cuda):
+    """Signals the presample cannot predict (a burst after silence, a 30-binade jump, leading zeros, a wrong
+    predicted mean): the device chain must either produce the exact sum or decline (sum_path == 2) - and the
+    reported sum is the sequential sum either way."""
+    n = (1 << 20) + 77
+    cases = {}
+    z = fixtures.siggen(0, n, 41).copy()
+    z[: 2 * 300_000] = 0.0
+    cases["leading_zeros"] = z
+    b = (fixtures.siggen(0, n, 42) * np.float32(1e-4)).astype(np.float32)
+    b[2 * 700_000:] *= np.float32(3e4)
+    cases["burst"] = b
+    j = fixtures.siggen(0, n, 43).copy()
+    j[2 * 500_000] = 1e15
+    cases["jump"] = j
+    eng.set("mode", 2)
+    try:
+        for name, f in cases.items():
+            st, *_ = oracle_binding.analyze(f, False)
+            res = eng.analyze_device(_dev(torch_cuda, f), n, False)
+            assert res.sum_path & 0xff in (1, 2), name
+            assert _bits(res.stats.sum) == _bits(st.sum), name
+            assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), False), name
+        f = fixtures.siggen(0, n, 44)
+        st, *_ = oracle_binding.analyze(f, False)
+        for bias in (0.5, 1.9, 4.0):
+            eng.set("predict_bias", bias)
+            res = eng.analyze_device(_dev(torch_cuda, f), n, False)
+            assert _bits(res.stats.sum) == _bits(st.sum), bias
+            assert built.format_result(res) == oracle_binding.run_image(f.tobytes(), False), bias
+    finally:
+        eng.set("predict_bias", 1.0)
+        eng.set("mode", 0)
