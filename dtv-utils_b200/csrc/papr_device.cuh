@@ -116,13 +116,12 @@ struct PaprScanArgs {
 
 struct PaprTileRun { double e0, e1; };                         // increments for an even / odd entry state
 
+#define XT_SUPER_CAND 3
 struct PaprSuperRec {                                          // 32 tiles composed (papr_xt_compose_kernel)
-    double e0, e1;
     double asum;                                               // approximate sum of the super-tile's powers
-    int code;                                                  // k + XT_KBIAS if all tiles share one binade, XT_SUPER_*
-    int pad;
+    int k_lo, nc;                                              // binades every tile of it has a run for: k_lo .. k_lo+nc-1
+    PaprTileRun r[XT_SUPER_CAND];                              // ... and the composed run for each of them
 };
-enum { XT_SUPER_COMPLEX = -1, XT_SUPER_EMPTY = -2 };
 
 struct PaprExactArgs {
     unsigned long long g_first;    // whole-capture index of this launch's sample 0 (prediction of the running sum)
@@ -131,6 +130,7 @@ struct PaprExactArgs {
     PaprTileRun *tile_run;         // [ntiles]
     int *tile_code;                // [ntiles]
     PaprTileRun *multi;            // [multi_cap][XT_MAX_CAND][XT_TILE_BATCHES] per-batch runs of the multi tiles
+    PaprTileRun *multi_tile;       // [multi_cap][XT_MAX_CAND] the same composed over the tile
     unsigned *multi_count;
     unsigned multi_cap;
 };
@@ -235,8 +235,8 @@ void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, P
 int papr_scan_tma_configure(void);
 void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, const PaprScanArgs &a, const PaprExactArgs &x,
                           cudaStream_t s);
-void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi,
-                            PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s);
+void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles,
+                            const PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s);
 void papr_launch_xt_chain(const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
                           const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
                           PaprChainList *out /* two lists back to back: [0] result, [1] scratch */, cudaStream_t s);

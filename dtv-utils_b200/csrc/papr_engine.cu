@@ -528,7 +528,7 @@ static int enqueue_scan_tma(papr_engine *e, const float *d_iq, u64 n, u64 first,
         x.tile_base = (unsigned)(off / XT_TILE_SAMPLES);
         x.literal_tile0 = first + off == 0;
         x.tile_run = e->d_xt_run; x.tile_code = e->d_xt_code;
-        x.multi = e->d_xt_multi; x.multi_count = e->d_xt_multi_count; x.multi_cap = e->xt_multi_cap;
+        x.multi = e->d_xt_multi; x.multi_tile = e->d_xt_multi_tile; x.multi_count = e->d_xt_multi_count; x.multi_cap = e->xt_multi_cap;
         CUtensorMap tm; // rows of 128 bytes (16 samples); the < 16 samples past the last full row are patched in by the kernel
         const cuuint64_t dims[2] = {32, std::max<u64>(m / 16, 1)};
         const cuuint64_t strides[1] = {128};
@@ -553,7 +553,7 @@ static int enqueue_xt_chain(papr_engine *e, const float *d_iq, u64 n)
 {
     const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
     const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
-    papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi, e->d_xt_multi_tile, e->d_xt_super,
+    papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super,
                            (int)std::min<unsigned>((nsuper + 7) / 8, (unsigned)e->num_sms * 8), e->stream);
     papr_launch_xt_chain(e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles, d_iq, n,
                          e->d_xt_chain, e->stream);

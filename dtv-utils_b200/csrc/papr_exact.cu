@@ -127,13 +127,33 @@ __device__ __forceinline__ XtLink xt_link(unsigned b0, unsigned b1, unsigned lt)
     return l;
 }
 
+// first sample of the batch (position inside it) whose tracked value equals the warp-wide maximum w
+template <int T>
+__device__ __forceinline__ unsigned xt_locate(const float4 (&r)[4], int w, int lane)
+{
+    unsigned pos = 0xffffffffu;
+#pragma unroll
+    for (int u = 3; u >= 0; --u) {
+        float v0 = power_of(r[u].x, r[u].y), v1 = power_of(r[u].z, r[u].w), a, b;
+        track_vals<T>(r[u], v0, v1, a, b);
+        const unsigned p = 8u * (unsigned)lane + 2u * (unsigned)u;
+        if (__float_as_int(b) == w) pos = p + 1;
+        if (__float_as_int(a) == w) pos = p;
+    }
+    return __reduce_min_sync(FULL, pos);
+}
+
 __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                         const PaprScanArgs a, const PaprExactArgs x)
 {
-    ScanState<true, true> st;
+    ScanState<true, true> st; // the CCDF fields; the extremes live in run_val[] + shared memory (rarely written)
     __shared__ __align__(8) unsigned long long s_bar[PAPR_WARPS];
+    __shared__ unsigned s_pos[PAPR_NTRACK][PAPR_WARPS]; // sample offset (inside this launch) of the warp's current first occurrences
+    __shared__ int s_val[PAPR_NTRACK][PAPR_WARPS];      // ... and their values; 0 = nothing new from this warp
+    __shared__ PaprTileRun s_mt[PAPR_WARPS][XT_MAX_CAND];
     unsigned *s_hist = reinterpret_cast<unsigned *>(scan_smem);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0); // warp-uniform for the compiler: TMA operands stay in uniform registers
     const unsigned lt = (1u << lane) - 1u;
 
     const PaprPlan pl = *a.plan;
@@ -152,30 +172,30 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
             s_fb[i] = (i >= 1 && i <= st.ncells) ? a.fine_base[i - 1] : 0u;
         }
     }
-    st.upd = 0;
 #pragma unroll
     for (int t = 0; t < PAPR_NTRACK; ++t) {
-        st.run_val[t] = a.wp[blockIdx.x].val[t];
-        st.run_pos[t] = 0;
+        st.run_val[t] = a.wp[blockIdx.x].val[t]; // carried over from earlier launches of this shard
+        if (lane == 0) { s_val[t][warp] = 0; s_pos[t][warp] = 0xffffffffu; }
     }
     const unsigned ring = (smem_u32(scan_smem) + SCAN_SMEM_BYTES + 1023u) & ~1023u;
-    const unsigned my = ring + warp * 2048u, bar = smem_u32(&s_bar[warp]);
+    const unsigned my = ring + (unsigned)warp * 2048u, bar = smem_u32(&s_bar[warp]);
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    // this lane's run: samples 8*lane .. 8*lane+7 of the batch = half a 128-byte row
-    unsigned off[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const unsigned row = lane >> 1, c = 4u * (lane & 1) + u;
-        off[u] = my + row * 128u + ((c ^ (row & 7u)) << 4);
+    // this lane's run: samples 8*lane .. 8*lane+7 of the batch = half a 128-byte row; its four 16-byte pieces
+    // sit at off0 ^ 0, 16, 32, 48 (128-byte swizzle: chunk index XOR row % 8)
+    unsigned off0;
+    {
+        const unsigned row = lane >> 1, c = 4u * (lane & 1);
+        off0 = my + row * 128u + ((c ^ (row & 7u)) << 4);
     }
 
     const u64 n = a.nsamples;
     const unsigned nbatch = (unsigned)((n + PAPR_BATCH_SAMPLES - 1) / PAPR_BATCH_SAMPLES);
     const unsigned ntiles = (nbatch + XT_TILE_BATCHES - 1) / XT_TILE_BATCHES;
-    const unsigned full_rows = (unsigned)(n >> 4), tail_n = (unsigned)(n & 15); // the tensor map covers the full rows
+    // the tensor map covers the full 128-byte rows; the < 16 samples past the last one are patched into this batch
+    const unsigned tail_n = (unsigned)(n & 15), tail_batch = tail_n ? (unsigned)(n >> 8) : 0xffffffffu;
     const unsigned tstride = gridDim.x * XT_SUPER_TILES;
     unsigned phase = 0;
     double wsum = 0.0; // lane 0: approximate sum of this warp's tiles (what the tree sum used to be)
@@ -194,74 +214,92 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
             slot = __shfl_sync(FULL, slot, 0);
             if (slot >= x.multi_cap) nc = 0; // log full: the chain falls back if this tile matters
         }
-        double A0 = 0.0, A1 = 0.0;   // nc == 1: this lane's share of the tile's increment, even / odd tile entry
-        unsigned P0 = 0, P1 = 1;     //          parity of the running state under the two hypotheses
-        double aux = 0.0;            // lane 0 (multi / literal) or every lane (unknown): approximate sum
-        const double c0 = xt_base(k_lo, 0), c1 = xt_base(k_lo, 1);
+        // nc == 1: this lane's share of the tile's increment for an even (A0) / odd (A1) tile entry;
+        // otherwise A0 is the approximate sum (lane 0: multi / literal, every lane: unknown)
+        double A0 = 0.0, A1 = 0.0;
+        unsigned P = 2u; // bit 0 / bit 1: parity of the running state under the two hypotheses
+        if (lane == 0) // multi tiles: the tile's run per candidate, composed batch by batch (rare: shared memory)
+            for (int cd = 0; cd < XT_MAX_CAND; ++cd) s_mt[warp][cd].e0 = s_mt[warp][cd].e1 = 0.0;
         const unsigned b_first = tile * XT_TILE_BATCHES;
         const unsigned nb = min((unsigned)XT_TILE_BATCHES, nbatch - b_first);
         for (unsigned b = 0; b < nb; ++b) {
             mbar_wait(bar, phase);
             phase ^= 1;
-            const unsigned row0 = (b_first + b) * 16u;
-            if (tail_n && full_rows >= row0 && full_rows < row0 + 16u) { // < 16 samples past the last full row
+            if (b_first + b == tail_batch) {
                 if ((unsigned)lane < tail_n) {
-                    const u64 s = ((u64)full_rows << 4) + lane;
+                    const u64 s = (n & ~15ull) + lane;
                     const float2 h = *reinterpret_cast<const float2 *>(a.iq + 2 * s);
                     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(my + xt_sample_off((unsigned)(s & 255))), "f"(h.x), "f"(h.y) : "memory");
                 }
                 __syncwarp();
             }
             float4 r[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) r[u] = lds128(off[u]);
+            r[0] = lds128(off0);
+            r[1] = lds128(off0 ^ 16u);
+            r[2] = lds128(off0 ^ 32u);
+            r[3] = lds128(off0 ^ 48u);
             if (literal) { // papr.c:103-104 as written, from a running sum of exactly 0
                 if (lane == 0) {
                     for (unsigned i = 0; i < PAPR_BATCH_SAMPLES; ++i) {
                         float2 h;
                         asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "r"(my + xt_sample_off(i)));
-                        aux = __dadd_rn(aux, (double)power_of(h.x, h.y));
+                        A0 = __dadd_rn(A0, (double)power_of(h.x, h.y));
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) { // the buffer is free again: fetch the next batch (of this tile or of the next one)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the warp's reads above vs the TMA write below
-                if (b + 1 < nb) tma_batch(my, &tmap, (int)(row0 + 16u), bar);
-                else if (tile + tstride < ntiles) tma_batch(my, &tmap, (int)((tile + tstride) * XT_TILE_BATCHES * 16), bar);
-            }
 
-            // ---- per-sample work: power, extremes, CCDF cells
+            // ---- power and extremes (papr.c:103,105-126)
             float v[8];
-            float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 q = r[u];
-                v[2 * u] = power_of(q.x, q.y);
-                v[2 * u + 1] = power_of(q.z, q.w);
-                bm0 = fmaxf(bm0, fmaxf(v[2 * u], v[2 * u + 1]));
-                bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
-                bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
-                bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
-                bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
-                hist_pair(st, v[2 * u], v[2 * u + 1]);
-            }
             {
+                float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 q = r[u];
+                    v[2 * u] = power_of(q.x, q.y);
+                    v[2 * u + 1] = power_of(q.z, q.w);
+                    bm0 = fmaxf(bm0, fmaxf(v[2 * u], v[2 * u + 1]));
+                    bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
+                    bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
+                    bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
+                    bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
+                }
                 const bool cand = __float_as_int(bm0) > st.run_val[TR_PEAK] || __float_as_int(bm1) > st.run_val[TR_RE_POS] ||
                                   __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
                                   __float_as_int(bm4) > st.run_val[TR_IM_NEG];
-                if (__any_sync(FULL, cand)) {
+                if (__any_sync(FULL, cand)) { // warp-uniform and rare after the first few batches
                     const unsigned batch_off = (b_first + b) * PAPR_BATCH_SAMPLES;
-                    track_update<TR_PEAK, true, true, true>(st, r, bm0, batch_off, lane);
-                    track_update<TR_RE_POS, true, true, true>(st, r, bm1, batch_off, lane);
-                    track_update<TR_RE_NEG, true, true, true>(st, r, bm2, batch_off, lane);
-                    track_update<TR_IM_POS, true, true, true>(st, r, bm3, batch_off, lane);
-                    track_update<TR_IM_NEG, true, true, true>(st, r, bm4, batch_off, lane);
+                    const float bm[PAPR_NTRACK] = {bm0, bm1, bm2, bm3, bm4};
+#pragma unroll
+                    for (int t = 0; t < PAPR_NTRACK; ++t) {
+                        const int w = __reduce_max_sync(FULL, __float_as_int(bm[t]));
+                        if (w > st.run_val[t]) {
+                            unsigned pos;
+                            if (t == TR_PEAK) pos = xt_locate<TR_PEAK>(r, w, lane);
+                            else if (t == TR_RE_POS) pos = xt_locate<TR_RE_POS>(r, w, lane);
+                            else if (t == TR_RE_NEG) pos = xt_locate<TR_RE_NEG>(r, w, lane);
+                            else if (t == TR_IM_POS) pos = xt_locate<TR_IM_POS>(r, w, lane);
+                            else pos = xt_locate<TR_IM_NEG>(r, w, lane);
+                            st.run_val[t] = w;
+                            if (lane == 0) { s_val[t][warp] = w; s_pos[t][warp] = batch_off + pos; }
+                        }
+                    }
                 }
             }
+            // every value of the batch has been consumed from the buffer (r[] is in registers): fetch the next
+            // batch of this tile, or the first one of this warp's next tile
+            __syncwarp();
+            if (lane == 0) {
+                if (b + 1 < nb) tma_batch(my, &tmap, (int)((b_first + b + 1) * 16u), bar);
+                else if (tile + tstride < ntiles) tma_batch(my, &tmap, (int)((tile + tstride) * XT_TILE_BATCHES * 16), bar);
+            }
+
+            // ---- CCDF cells (papr.c:147-151)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) hist_pair(st, v[2 * u], v[2 * u + 1]);
 
             // ---- papr.c:104
             if (nc == 1) {
+                const double c0 = xt_base(k_lo, 0), c1 = xt_base(k_lo, 1);
                 double a0 = c0, a1 = c1;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -269,15 +307,14 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                     a0 = __dadd_rn(a0, d);
                     a1 = __dadd_rn(a1, d);
                 }
-                const unsigned b0 = __ballot_sync(FULL, xt_lsb(a0)), b1 = __ballot_sync(FULL, xt_lsb(a1));
-                const XtLink l = xt_link(b0, b1, lt);
+                const unsigned x0 = xt_lsb(a0), x1 = xt_lsb(a1);
+                const XtLink l = xt_link(__ballot_sync(FULL, x0), __ballot_sync(FULL, x1), lt);
                 const double i0 = __dsub_rn(a0, c0), i1 = __dsub_rn(a1, c1);
-                const unsigned p0 = (l.fixed ? l.base : P0) ^ l.flip, p1 = (l.fixed ? l.base : P1) ^ l.flip;
+                const unsigned p0 = (l.fixed ? l.base : (P & 1u)) ^ l.flip, p1 = (l.fixed ? l.base : (P >> 1)) ^ l.flip;
                 A0 = __dadd_rn(A0, p0 ? i1 : i0);
                 A1 = __dadd_rn(A1, p1 ? i1 : i0);
-                const XtLink e = xt_link(b0, b1, 0xffffffffu); // "lane 32": the parity the next batch is entered with
-                P0 = (e.fixed ? e.base : P0) ^ e.flip;
-                P1 = (e.fixed ? e.base : P1) ^ e.flip;
+                // the parity with which the next batch is entered = lane 31's exit parity under each hypothesis
+                P = __shfl_sync(FULL, (p0 ? x1 : x0) | ((p1 ? x1 : x0) << 1), 31);
             } else if (nc > 1) { // one run per candidate binade and per batch, for the chain to choose from
                 for (int cd = 0; cd < nc; ++cd) {
                     const double d0 = xt_base(k_lo + cd, 0), d1 = xt_base(k_lo + cd, 1);
@@ -288,21 +325,21 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                         a0 = __dadd_rn(a0, d);
                         a1 = __dadd_rn(a1, d);
                     }
-                    const unsigned b0 = __ballot_sync(FULL, xt_lsb(a0)), b1 = __ballot_sync(FULL, xt_lsb(a1));
-                    const XtLink l = xt_link(b0, b1, lt);
+                    const XtLink l = xt_link(__ballot_sync(FULL, xt_lsb(a0)), __ballot_sync(FULL, xt_lsb(a1)), lt);
                     const double i0 = __dsub_rn(a0, d0), i1 = __dsub_rn(a1, d1);
                     const unsigned p0 = (l.fixed ? l.base : 0u) ^ l.flip, p1 = (l.fixed ? l.base : 1u) ^ l.flip;
-                    const double B0 = warp_sum_fixed(p0 ? i1 : i0), B1 = warp_sum_fixed(p1 ? i1 : i0);
+                    PaprTileRun br;
+                    br.e0 = warp_sum_fixed(p0 ? i1 : i0);
+                    br.e1 = warp_sum_fixed(p1 ? i1 : i0);
                     if (lane == 0) {
-                        PaprTileRun br;
-                        br.e0 = B0; br.e1 = B1;
                         x.multi[((size_t)slot * XT_MAX_CAND + cd) * XT_TILE_BATCHES + b] = br;
-                        if (cd == 0) aux = __dadd_rn(aux, B0);
+                        if (cd == 0) A0 = __dadd_rn(A0, br.e0);
+                        s_mt[warp][cd] = xt_compose(s_mt[warp][cd], br, k_lo + cd);
                     }
                 }
             } else if (!literal) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) aux = __dadd_rn(aux, (double)v[j]);
+                for (int j = 0; j < 8; ++j) A0 = __dadd_rn(A0, (double)v[j]);
             }
         }
 
@@ -313,9 +350,8 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
             tr.e0 = warp_sum_fixed(A0);
             tr.e1 = warp_sum_fixed(A1);
             code = (k_lo + XT_KBIAS) | (1 << 12);
-            if (lane == 0) wsum = __dadd_rn(wsum, tr.e0);
         } else if (nc > 1) {
-            tr.e0 = aux; tr.e1 = 0.0;
+            tr.e0 = A0; tr.e1 = 0.0;
             code = (k_lo + XT_KBIAS) | (nc << 12) | (int)(slot << 16);
             if (lane == 0) {
                 PaprTileRun z;
@@ -323,18 +359,17 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                 for (int cd = 0; cd < nc; ++cd)
                     for (unsigned b = nb; b < XT_TILE_BATCHES; ++b)
                         x.multi[((size_t)slot * XT_MAX_CAND + cd) * XT_TILE_BATCHES + b] = z;
-                wsum = __dadd_rn(wsum, aux);
+                for (int cd = 0; cd < nc; ++cd) x.multi_tile[(size_t)slot * XT_MAX_CAND + cd] = s_mt[warp][cd];
             }
         } else if (literal) {
-            tr.e0 = tr.e1 = aux;
+            tr.e0 = tr.e1 = A0;
             code = XT_CODE_LITERAL;
-            if (lane == 0) wsum = __dadd_rn(wsum, aux);
         } else {
-            tr.e0 = warp_sum_fixed(aux); tr.e1 = 0.0;
+            tr.e0 = warp_sum_fixed(A0); tr.e1 = 0.0;
             code = 0;
-            if (lane == 0) wsum = __dadd_rn(wsum, tr.e0);
         }
         if (lane == 0) {
+            wsum = __dadd_rn(wsum, tr.e0);
             x.tile_run[x.tile_base + tile] = tr;
             x.tile_code[x.tile_base + tile] = code;
         }
@@ -343,17 +378,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
     // ---- CTA-level fold of the warps' states (fixed order), then into the CTA's persistent partial
     {
         __shared__ double s_wsum[PAPR_WARPS];
-        __shared__ int s_wval[PAPR_NTRACK][PAPR_WARPS];
-        __shared__ unsigned s_wpos[PAPR_NTRACK][PAPR_WARPS];
-        if (lane == 0) {
-            s_wsum[warp] = wsum;
-#pragma unroll
-            for (int t = 0; t < PAPR_NTRACK; ++t) {
-                const bool u = (st.upd >> t) & 1u;
-                s_wval[t][warp] = u ? st.run_val[t] : 0;
-                s_wpos[t][warp] = u ? st.run_pos[t] : 0xffffffffu;
-            }
-        }
+        if (lane == 0) s_wsum[warp] = wsum;
         __syncthreads();
         if (warp == 0) {
             double xs = warp_sum_fixed(lane < PAPR_WARPS ? s_wsum[lane] : 0.0);
@@ -361,11 +386,11 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
             if (lane == 0) w->sum += xs;
 #pragma unroll
             for (int t = 0; t < PAPR_NTRACK; ++t) {
-                int vv = lane < PAPR_WARPS ? s_wval[t][lane] : 0;
-                unsigned pos = lane < PAPR_WARPS ? s_wpos[t][lane] : 0xffffffffu;
+                int vv = lane < PAPR_WARPS ? s_val[t][lane] : 0;
+                unsigned pos = lane < PAPR_WARPS ? s_pos[t][lane] : 0xffffffffu;
                 const int vmax = __reduce_max_sync(FULL, vv);
                 const unsigned pmin = __reduce_min_sync(FULL, vv == vmax ? pos : 0xffffffffu);
-                if (lane == 0 && vmax > w->val[t]) {
+                if (lane == 0 && vmax > w->val[t]) { // strictly greater than what earlier launches left: first occurrence kept
                     w->val[t] = vmax;
                     w->idx[t] = a.first_index + pmin;
                 }
@@ -412,9 +437,11 @@ __device__ __forceinline__ PaprTileRun xt_warp_compose(PaprTileRun r, int k)
     return r;
 }
 
+// one warp per super-tile, one lane per tile: for every binade that ALL its tiles have a run for, the
+// ordered composition of the 32 runs
 __global__ void __launch_bounds__(256) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
-                                                              unsigned ntiles, const PaprTileRun *multi,
-                                                              PaprTileRun *multi_tile, PaprSuperRec *super)
+                                                              unsigned ntiles, const PaprTileRun *multi_tile,
+                                                              PaprSuperRec *super)
 {
     const int lane = threadIdx.x & 31;
     const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -426,36 +453,36 @@ __global__ void __launch_bounds__(256) papr_xt_compose_kernel(const PaprTileRun 
         PaprTileRun run;
         run.e0 = run.e1 = 0.0;
         if (have) run = tile_run[t];
-        const int nc = have ? XT_CODE_NC(code) : 0, k = XT_CODE_K(code);
+        const int nc = have ? XT_CODE_NC(code) : 0, K = XT_CODE_K(code);
         const double asum = run.e0;
-        if (nc > 1) {
-            const PaprTileRun *m = multi + (size_t)XT_CODE_SLOT(code) * XT_MAX_CAND * XT_TILE_BATCHES;
-            for (int cd = 0; cd < nc; ++cd) {
-                PaprTileRun r = m[cd * XT_TILE_BATCHES];
-                for (int b = 1; b < XT_TILE_BATCHES; ++b) r = xt_compose(r, m[cd * XT_TILE_BATCHES + b], k + cd);
-                multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + cd] = r;
+        // candidate binades of this tile; an all-zero tile (or none at all) is the identity in every binade
+        const bool ident = !have || (!(code & XT_CODE_LITERAL) && asum == 0.0);
+        int lo = ident ? -5000 : (nc >= 1 ? K : 5000), hi = ident ? 5000 : (nc >= 1 ? K + nc - 1 : -5000);
+        lo = __reduce_max_sync(FULL, lo);
+        hi = __reduce_min_sync(FULL, hi);
+        const int ncs = lo == -5000 ? 0 : max(0, min(hi - lo + 1, XT_SUPER_CAND)); // all identity: nothing to record
+        PaprSuperRec s;
+        s.k_lo = lo; s.nc = ncs;
+#pragma unroll
+        for (int cd = 0; cd < XT_SUPER_CAND; ++cd) {
+            s.r[cd].e0 = s.r[cd].e1 = 0.0;
+            if (cd < ncs) {
+                const int k = lo + cd;
+                PaprTileRun r;
+                r.e0 = r.e1 = 0.0;
+                if (!ident) r = nc == 1 ? run : multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (k - K)];
+                s.r[cd] = xt_warp_compose(r, k);
             }
         }
-        const unsigned real = __ballot_sync(FULL, have);
-        const int kk = __shfl_sync(FULL, k, __ffs(real) - 1);
-        const bool simple = __all_sync(FULL, !have || (nc == 1 && k == kk)) && real != 0;
-        if (!simple) run.e0 = run.e1 = 0.0;
-        const PaprTileRun total = xt_warp_compose(run, kk);
-        const double at = warp_sum_fixed(asum);
-        if (lane == 0) {
-            PaprSuperRec s;
-            s.e0 = total.e0; s.e1 = total.e1; s.asum = at;
-            s.code = simple ? kk + XT_KBIAS : (real ? XT_SUPER_COMPLEX : XT_SUPER_EMPTY);
-            s.pad = 0;
-            super[st] = s;
-        }
+        s.asum = warp_sum_fixed(asum);
+        if (lane == 0) super[st] = s;
     }
 }
 
-void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi,
-                            PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s)
+void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi_tile,
+                            PaprSuperRec *super, int grid, cudaStream_t s)
 {
-    papr_xt_compose_kernel<<<grid, 256, 0, s>>>(tile_run, tile_code, ntiles, multi, multi_tile, super);
+    papr_xt_compose_kernel<<<grid, 256, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -631,17 +658,9 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
                 k = xt_expo(p);
                 continue;
             }
-            if (sr.code == k + XT_KBIAS) {
-                PaprTileRun r;
-                r.e0 = sr.e0; r.e1 = sr.e1;
-                cur = xt_compose(cur, r, k);
-            } else if (sr.code == XT_SUPER_COMPLEX) {
-                for (unsigned tt = 0; tt < XT_SUPER_TILES; ++tt) {
-                    PaprTileRun r;
-                    if (!xt_tile_rec(c, i * XT_SUPER_TILES + tt, k, &r)) { fail(XW_TILE_NO_CANDIDATE); break; }
-                    cur = xt_compose(cur, r, k);
-                }
-            } else if (sr.code != XT_SUPER_EMPTY && !(sr.asum == 0.0)) {
+            if (sr.nc > 0 && k >= sr.k_lo && k < sr.k_lo + sr.nc) {
+                cur = xt_compose(cur, sr.r[k - sr.k_lo], k);
+            } else if (!(sr.asum == 0.0)) { // (nothing but zeros: the identity in any binade)
                 fail(XW_SUPER_MISPREDICTED);
             }
             p += sr.asum;
