@@ -94,15 +94,17 @@ struct PaprScanArgs {
 };
 
 // ---- the reference's SEQUENTIAL double sum (papr.c:104) inside the fused scan (papr_exact.cu) -------
-// The TMA-fed scan gives every lane 8 consecutive samples per warp batch and every warp whole "tiles"
-// of 16 batches; per tile it emits a RUN - the increment of the running sum for an even and for an odd
+// The TMA-fed scan gives every lane 16 consecutive samples per warp batch and every warp whole "tiles"
+// of 8 batches; per tile it emits a RUN - the increment of the running sum for an even and for an odd
 // entry state, valid inside one binade [2^k, 2^(k+1)) of the running sum (see papr_seqsum_kernel).  k is
 // predicted per tile from the presample mean; tiles that may straddle a power of two carry one run per
 // candidate binade and per batch ("multi" tiles).  A single-CTA kernel then chains everything in file
-// order, resolving each binade crossing down to the 8 samples in which it happens.
-#define XT_TILE_BATCHES 16
-#define XT_TILE_SAMPLES (XT_TILE_BATCHES * PAPR_BATCH_SAMPLES) // 4096 samples = 32 KiB per warp tile
-#define XT_SUPER_TILES PAPR_WARPS                              // 32 tiles = 1 MiB per CTA iteration
+// order, resolving each binade crossing down to the 16 samples in which it happens.
+#define XT_RUN 16                                              // consecutive samples per lane and batch (one 128-byte row)
+#define XT_BATCH_SAMPLES (32 * XT_RUN)                         // 512 samples = 4 KiB = one TMA box of 32 rows
+#define XT_TILE_BATCHES 8
+#define XT_TILE_SAMPLES (XT_TILE_BATCHES * XT_BATCH_SAMPLES)   // 4096 samples = 32 KiB per warp tile
+#define XT_SUPER_TILES 32                                      // tiles per super-tile record (one lane each in the compose kernel)
 #define XT_SUPER_SAMPLES (XT_SUPER_TILES * XT_TILE_SAMPLES)
 #define XT_MAX_CAND 4                                          // candidate binades of a multi tile
 #define XT_KBIAS 1100                                          // tile code: k + XT_KBIAS in bits 0-11 ...
@@ -138,9 +140,9 @@ struct PaprExactArgs {
 // what the chain of one shard boils down to: a short list of items applied in order to the running sum
 enum { XT_IT_SEG = 1, XT_IT_LIT = 2, XT_IT_ABS = 3 };
 struct PaprChainItem {
-    int type;       // SEG: a run (d[0], d[1]) valid in binade k; LIT: 8 powers added literally, ending in binade k;
+    int type;       // SEG: a run (d[0], d[1]) valid in binade k; LIT: XT_RUN powers added literally, ending in binade k;
     int k;          // ABS: the running sum becomes d[0] (valid for an entry state of exactly 0)
-    double d[8];
+    double d[XT_RUN];
 };
 enum { XT_OK = 0, XT_FALLBACK = 1, XT_NONFINITE = 2 };
 struct PaprChainList {

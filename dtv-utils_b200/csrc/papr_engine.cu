@@ -532,7 +532,7 @@ static int enqueue_scan_tma(papr_engine *e, const float *d_iq, u64 n, u64 first,
         CUtensorMap tm; // rows of 128 bytes (16 samples); the < 16 samples past the last full row are patched in by the kernel
         const cuuint64_t dims[2] = {32, std::max<u64>(m / 16, 1)};
         const cuuint64_t strides[1] = {128};
-        const cuuint32_t box[2] = {32, 16}, es[2] = {1, 1};
+        const cuuint32_t box[2] = {32, 32}, es[2] = {1, 1}; // 32 rows x 128 B = one 4 KiB warp batch
         CUresult r = tensor_map_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)(d_iq + 2 * off), dims, strides, box, es,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

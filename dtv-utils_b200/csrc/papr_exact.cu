@@ -66,12 +66,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
                      : "=r"(done) : "r"(bar), "r"(phase) : "memory");
 }
 
-// one 2 KiB box: rows [row, row+16) x 128 B of the capture -> swizzled shared memory, completion on `bar`
+// one 4 KiB box: rows [row, row+32) x 128 B of the capture -> swizzled shared memory, completion on `bar`.
+// Called by the whole (converged) warp; one elected lane arms the barrier and issues the copy.
 __device__ __forceinline__ void tma_batch(unsigned dst, const CUtensorMap *tm, int row, unsigned bar)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2048) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(tm), "r"(0), "r"(row), "r"(bar) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 4096;\n\t"
+                 "@p cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%3, %4}], [%0];\n\t"
+                 "}" ::"r"(bar), "r"(dst), "l"(tm), "r"(0), "r"(row) : "memory");
 }
 
 __device__ __forceinline__ float4 lds128(unsigned addr)
@@ -81,7 +84,7 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
     return r;
 }
 
-// byte offset of sample i (0..255) of a batch inside its swizzled 2 KiB box
+// byte offset of sample i (0..511) of a batch inside its swizzled 4 KiB box
 __device__ __forceinline__ unsigned xt_sample_off(unsigned i)
 {
     const unsigned row = i >> 4, chunk = (i >> 1) & 7;
@@ -105,7 +108,11 @@ __device__ __forceinline__ int xt_candidates(double avg, double window, double w
 // ------------------------------------------------------------------------------------------------
 // the fused scan
 // ------------------------------------------------------------------------------------------------
-#define XT_RING_BYTES (PAPR_WARPS * 2048)
+#ifndef XT_THREADS
+#define XT_THREADS 640 // 20 warps x 4 KiB in flight; ~100 registers per thread
+#endif
+#define XT_WARPS (XT_THREADS / 32)
+#define XT_RING_BYTES (XT_WARPS * 4096)
 #define XT_SMEM_BYTES (SCAN_SMEM_BYTES + 1024 + XT_RING_BYTES)
 
 // entry parity of this lane's run given the exit parities of the lower lanes (b0 / b1: ballots of the exit
@@ -129,28 +136,28 @@ __device__ __forceinline__ XtLink xt_link(unsigned b0, unsigned b1, unsigned lt)
 
 // first sample of the batch (position inside it) whose tracked value equals the warp-wide maximum w
 template <int T>
-__device__ __forceinline__ unsigned xt_locate(const float4 (&r)[4], int w, int lane)
+__device__ __forceinline__ unsigned xt_locate(const float4 (&r)[XT_RUN / 2], int w, int lane)
 {
     unsigned pos = 0xffffffffu;
 #pragma unroll
-    for (int u = 3; u >= 0; --u) {
+    for (int u = XT_RUN / 2 - 1; u >= 0; --u) {
         float v0 = power_of(r[u].x, r[u].y), v1 = power_of(r[u].z, r[u].w), a, b;
         track_vals<T>(r[u], v0, v1, a, b);
-        const unsigned p = 8u * (unsigned)lane + 2u * (unsigned)u;
+        const unsigned p = (unsigned)XT_RUN * (unsigned)lane + 2u * (unsigned)u;
         if (__float_as_int(b) == w) pos = p + 1;
         if (__float_as_int(a) == w) pos = p;
     }
     return __reduce_min_sync(FULL, pos);
 }
 
-__global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                        const PaprScanArgs a, const PaprExactArgs x)
+__global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                      const PaprScanArgs a, const PaprExactArgs x)
 {
     ScanState<true, true> st; // the CCDF fields; the extremes live in run_val[] + shared memory (rarely written)
-    __shared__ __align__(8) unsigned long long s_bar[PAPR_WARPS];
-    __shared__ unsigned s_pos[PAPR_NTRACK][PAPR_WARPS]; // sample offset (inside this launch) of the warp's current first occurrences
-    __shared__ int s_val[PAPR_NTRACK][PAPR_WARPS];      // ... and their values; 0 = nothing new from this warp
-    __shared__ PaprTileRun s_mt[PAPR_WARPS][XT_MAX_CAND];
+    __shared__ __align__(8) unsigned long long s_bar[XT_WARPS];
+    __shared__ unsigned s_pos[PAPR_NTRACK][XT_WARPS]; // sample offset (inside this launch) of the warp's current first occurrences
+    __shared__ int s_val[PAPR_NTRACK][XT_WARPS];      // ... and their values; 0 = nothing new from this warp
+    __shared__ PaprTileRun s_mt[XT_WARPS][XT_MAX_CAND];
     unsigned *s_hist = reinterpret_cast<unsigned *>(scan_smem);
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0); // warp-uniform for the compiler: TMA operands stay in uniform registers
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
         st.cell_base = do_hist ? pl.cell_base : 0x7fffffff; // no valid plan: every sample lands in slot 0
         st.ncells = do_hist ? pl.ncells : 0;
         st.fmask = (1u << pl.sh) - 1u;
-        for (int i = threadIdx.x; i < st.ncells + 2; i += PAPR_THREADS) {
+        for (int i = threadIdx.x; i < st.ncells + 2; i += XT_THREADS) {
             s_hist[i] = 0;
             s_fb[i] = (i >= 1 && i <= st.ncells) ? a.fine_base[i - 1] : 0u;
         }
@@ -178,30 +185,26 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
         if (lane == 0) { s_val[t][warp] = 0; s_pos[t][warp] = 0xffffffffu; }
     }
     const unsigned ring = (smem_u32(scan_smem) + SCAN_SMEM_BYTES + 1023u) & ~1023u;
-    const unsigned my = ring + (unsigned)warp * 2048u, bar = smem_u32(&s_bar[warp]);
+    const unsigned my = ring + (unsigned)warp * 4096u, bar = smem_u32(&s_bar[warp]);
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    // this lane's run: samples 8*lane .. 8*lane+7 of the batch = half a 128-byte row; its four 16-byte pieces
-    // sit at off0 ^ 0, 16, 32, 48 (128-byte swizzle: chunk index XOR row % 8)
-    unsigned off0;
-    {
-        const unsigned row = lane >> 1, c = 4u * (lane & 1);
-        off0 = my + row * 128u + ((c ^ (row & 7u)) << 4);
-    }
+    // this lane's run: samples 16*lane .. 16*lane+15 of the batch = one 128-byte row; its eight 16-byte pieces
+    // sit at off0 ^ (j << 4) (128-byte swizzle: chunk index XOR row % 8)
+    const unsigned off0 = my + (unsigned)lane * 128u + (((unsigned)lane & 7u) << 4);
 
     const u64 n = a.nsamples;
-    const unsigned nbatch = (unsigned)((n + PAPR_BATCH_SAMPLES - 1) / PAPR_BATCH_SAMPLES);
+    const unsigned nbatch = (unsigned)((n + XT_BATCH_SAMPLES - 1) / XT_BATCH_SAMPLES);
     const unsigned ntiles = (nbatch + XT_TILE_BATCHES - 1) / XT_TILE_BATCHES;
     // the tensor map covers the full 128-byte rows; the < 16 samples past the last one are patched into this batch
-    const unsigned tail_n = (unsigned)(n & 15), tail_batch = tail_n ? (unsigned)(n >> 8) : 0xffffffffu;
-    const unsigned tstride = gridDim.x * XT_SUPER_TILES;
+    const unsigned tail_n = (unsigned)(n & 15), tail_batch = tail_n ? (unsigned)(n / XT_BATCH_SAMPLES) : 0xffffffffu;
+    const unsigned tstride = gridDim.x * XT_WARPS;
     unsigned phase = 0;
     double wsum = 0.0; // lane 0: approximate sum of this warp's tiles (what the tree sum used to be)
 
-    unsigned tile = blockIdx.x * XT_SUPER_TILES + warp;
-    if (tile < ntiles && lane == 0) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 16), bar);
+    unsigned tile = blockIdx.x * XT_WARPS + warp;
+    if (tile < ntiles) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 32), bar);
     for (; tile < ntiles; tile += tstride) {
         // ---- which binade(s) will the running sum be in while this tile is added?
         const u64 g0 = x.g_first + (u64)tile * XT_TILE_SAMPLES;
@@ -229,18 +232,16 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                 if ((unsigned)lane < tail_n) {
                     const u64 s = (n & ~15ull) + lane;
                     const float2 h = *reinterpret_cast<const float2 *>(a.iq + 2 * s);
-                    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(my + xt_sample_off((unsigned)(s & 255))), "f"(h.x), "f"(h.y) : "memory");
+                    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(my + xt_sample_off((unsigned)(s % XT_BATCH_SAMPLES))), "f"(h.x), "f"(h.y) : "memory");
                 }
                 __syncwarp();
             }
-            float4 r[4];
-            r[0] = lds128(off0);
-            r[1] = lds128(off0 ^ 16u);
-            r[2] = lds128(off0 ^ 32u);
-            r[3] = lds128(off0 ^ 48u);
+            float4 r[XT_RUN / 2];
+#pragma unroll
+            for (int u = 0; u < XT_RUN / 2; ++u) r[u] = lds128(off0 ^ (16u * u));
             if (literal) { // papr.c:103-104 as written, from a running sum of exactly 0
                 if (lane == 0) {
-                    for (unsigned i = 0; i < PAPR_BATCH_SAMPLES; ++i) {
+                    for (unsigned i = 0; i < XT_BATCH_SAMPLES; ++i) {
                         float2 h;
                         asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(h.x), "=f"(h.y) : "r"(my + xt_sample_off(i)));
                         A0 = __dadd_rn(A0, (double)power_of(h.x, h.y));
@@ -249,11 +250,11 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
             }
 
             // ---- power and extremes (papr.c:103,105-126)
-            float v[8];
+            float v[XT_RUN];
             {
                 float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < XT_RUN / 2; ++u) {
                     const float4 q = r[u];
                     v[2 * u] = power_of(q.x, q.y);
                     v[2 * u + 1] = power_of(q.z, q.w);
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                                   __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
                                   __float_as_int(bm4) > st.run_val[TR_IM_NEG];
                 if (__any_sync(FULL, cand)) { // warp-uniform and rare after the first few batches
-                    const unsigned batch_off = (b_first + b) * PAPR_BATCH_SAMPLES;
+                    const unsigned batch_off = (b_first + b) * XT_BATCH_SAMPLES;
                     const float bm[PAPR_NTRACK] = {bm0, bm1, bm2, bm3, bm4};
 #pragma unroll
                     for (int t = 0; t < PAPR_NTRACK; ++t) {
@@ -285,24 +286,23 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                     }
                 }
             }
-            // every value of the batch has been consumed from the buffer (r[] is in registers): fetch the next
-            // batch of this tile, or the first one of this warp's next tile
+            // the batch is in registers: fetch the next one of this tile, or the first one of this warp's next tile
             __syncwarp();
-            if (lane == 0) {
-                if (b + 1 < nb) tma_batch(my, &tmap, (int)((b_first + b + 1) * 16u), bar);
-                else if (tile + tstride < ntiles) tma_batch(my, &tmap, (int)((tile + tstride) * XT_TILE_BATCHES * 16), bar);
+            {
+                const unsigned nxt = b + 1 < nb ? b_first + b + 1 : (tile + tstride) * XT_TILE_BATCHES;
+                if (nxt < nbatch) tma_batch(my, &tmap, (int)(nxt * 32u), bar);
             }
 
             // ---- CCDF cells (papr.c:147-151)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) hist_pair(st, v[2 * u], v[2 * u + 1]);
+            for (int u = 0; u < XT_RUN / 2; ++u) hist_pair(st, v[2 * u], v[2 * u + 1]);
 
             // ---- papr.c:104
             if (nc == 1) {
                 const double c0 = xt_base(k_lo, 0), c1 = xt_base(k_lo, 1);
                 double a0 = c0, a1 = c1;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < XT_RUN; ++j) {
                     const double d = (double)v[j];
                     a0 = __dadd_rn(a0, d);
                     a1 = __dadd_rn(a1, d);
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                     const double d0 = xt_base(k_lo + cd, 0), d1 = xt_base(k_lo + cd, 1);
                     double a0 = d0, a1 = d1;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < XT_RUN; ++j) {
                         const double d = (double)v[j];
                         a0 = __dadd_rn(a0, d);
                         a1 = __dadd_rn(a1, d);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
                 }
             } else if (!literal) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) A0 = __dadd_rn(A0, (double)v[j]);
+                for (int j = 0; j < XT_RUN; ++j) A0 = __dadd_rn(A0, (double)v[j]);
             }
         }
 
@@ -377,17 +377,17 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
 
     // ---- CTA-level fold of the warps' states (fixed order), then into the CTA's persistent partial
     {
-        __shared__ double s_wsum[PAPR_WARPS];
+        __shared__ double s_wsum[XT_WARPS];
         if (lane == 0) s_wsum[warp] = wsum;
         __syncthreads();
         if (warp == 0) {
-            double xs = warp_sum_fixed(lane < PAPR_WARPS ? s_wsum[lane] : 0.0);
+            double xs = warp_sum_fixed(lane < XT_WARPS ? s_wsum[lane] : 0.0);
             PaprCtaPartial *w = a.wp + blockIdx.x;
             if (lane == 0) w->sum += xs;
 #pragma unroll
             for (int t = 0; t < PAPR_NTRACK; ++t) {
-                int vv = lane < PAPR_WARPS ? s_val[t][lane] : 0;
-                unsigned pos = lane < PAPR_WARPS ? s_pos[t][lane] : 0xffffffffu;
+                int vv = lane < XT_WARPS ? s_val[t][lane] : 0;
+                unsigned pos = lane < XT_WARPS ? s_pos[t][lane] : 0xffffffffu;
                 const int vmax = __reduce_max_sync(FULL, vv);
                 const unsigned pmin = __reduce_min_sync(FULL, vv == vmax ? pos : 0xffffffffu);
                 if (lane == 0 && vmax > w->val[t]) { // strictly greater than what earlier launches left: first occurrence kept
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_scan_tma_kernel(const __
     }
     if (do_hist) {
         __syncthreads();
-        for (int i = threadIdx.x; i < st.ncells; i += PAPR_THREADS) {
+        for (int i = threadIdx.x; i < st.ncells; i += XT_THREADS) {
             unsigned c = s_hist[i + 1];
             if (c) atomicAdd(&a.g_hist[i], (u64)c);
         }
@@ -414,7 +414,7 @@ int papr_scan_tma_configure(void)
 
 void papr_launch_scan_tma(const void *tmap, int grid, const PaprScanArgs &a, const PaprExactArgs &x, cudaStream_t s)
 {
-    papr_scan_tma_kernel<<<grid, PAPR_THREADS, XT_SMEM_BYTES, s>>>(*reinterpret_cast<const CUtensorMap *>(tmap), a, x);
+    papr_scan_tma_kernel<<<grid, XT_THREADS, XT_SMEM_BYTES, s>>>(*reinterpret_cast<const CUtensorMap *>(tmap), a, x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -546,7 +546,7 @@ __device__ int xt_walk(const PaprChainItem *item, int n, double *state, int *why
             s = s2;
         } else if (it.type == XT_IT_LIT) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s = __dadd_rn(s, it.d[j]); // papr.c:104 as written
+            for (int j = 0; j < XT_RUN; ++j) s = __dadd_rn(s, it.d[j]); // papr.c:104 as written
             if (xt_expo(s) != it.k) { *why = XW_WALK_LITERAL; return XT_FALLBACK; }
         } else {
             if (s != 0.0) { *why = XW_WALK_ABS; return XT_FALLBACK; }
@@ -586,7 +586,7 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
         if (i >= XT_MAX_ITEMS) { fail(XW_TOO_MANY_ITEMS); return; }
         scratch[i].type = type;
         scratch[i].k = k;
-        for (int j = 0; j < 8; ++j) scratch[i].d[j] = j < nd ? d[j] : 0.0;
+        for (int j = 0; j < XT_RUN; ++j) scratch[i].d[j] = j < nd ? d[j] : 0.0;
         s_key[i] = pos;
     };
 
@@ -774,14 +774,14 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             if (lane == 0) {
                 const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
                 emit(XT_IT_SEG, kb, tile_pos + 1, d, 2);                                  // after the tile-level stretch that ends here
-                emit(XT_IT_SEG, ka, tile_pos + (unsigned long long)(bx + 1) * PAPR_BATCH_SAMPLES, e, 2);
+                emit(XT_IT_SEG, ka, tile_pos + (unsigned long long)(bx + 1) * XT_BATCH_SAMPLES, e, 2);
             }
         }
         // the crossing batch: this lane's 8 samples, runs for both binades
-        const unsigned long long s0 = tile_pos + (unsigned long long)bx * PAPR_BATCH_SAMPLES + 8ull * lane;
-        double v[8];
+        const unsigned long long s0 = tile_pos + (unsigned long long)bx * XT_BATCH_SAMPLES + (unsigned long long)XT_RUN * lane;
+        double v[XT_RUN];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < XT_RUN; ++j) {
             v[j] = 0.0;
             if (s0 + j < c.nsamples) {
                 const float2 h = *reinterpret_cast<const float2 *>(c.iq + 2 * (s0 + j));
@@ -792,7 +792,7 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
         {
             double a0 = xt_base(kb, 0), a1 = xt_base(kb, 1), b0 = xt_base(ka, 0), b1 = xt_base(ka, 1);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < XT_RUN; ++j) {
                 a0 = __dadd_rn(a0, v[j]); a1 = __dadd_rn(a1, v[j]);
                 b0 = __dadd_rn(b0, v[j]); b1 = __dadd_rn(b1, v[j]);
             }
@@ -810,13 +810,13 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             PaprTileRun q = la;
             if (lane <= lx) q.e0 = q.e1 = 0.0;
             q = xt_warp_compose(q, ka);
-            const unsigned long long bpos = tile_pos + (unsigned long long)bx * PAPR_BATCH_SAMPLES;
+            const unsigned long long bpos = tile_pos + (unsigned long long)bx * XT_BATCH_SAMPLES;
             if (lane == 0) {
                 const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
                 emit(XT_IT_SEG, kb, bpos + 2, d, 2);
-                emit(XT_IT_SEG, ka, bpos + 8ull * (lx + 1), e, 2);
+                emit(XT_IT_SEG, ka, bpos + (unsigned long long)XT_RUN * (lx + 1), e, 2);
             }
-            if (lane == lx) emit(XT_IT_LIT, ka, bpos + 8ull * lx + 3, v, 8);
+            if (lane == lx) emit(XT_IT_LIT, ka, bpos + (unsigned long long)XT_RUN * lx + 3, v, XT_RUN);
         }
     }
     __syncthreads();
