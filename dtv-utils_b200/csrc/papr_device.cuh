@@ -106,15 +106,15 @@ struct PaprScanArgs {
 #define XT_TILE_SAMPLES (XT_TILE_BATCHES * XT_BATCH_SAMPLES)   // 4096 samples = 32 KiB per warp tile
 #define XT_SUPER_TILES 32                                      // tiles per super-tile record (one lane each in the compose kernel)
 #define XT_SUPER_SAMPLES (XT_SUPER_TILES * XT_TILE_SAMPLES)
+#define XT_HYPER_SUPERS 32                                     // super-tiles per hyper-tile record (4M samples)
+#define XT_HYPER_SAMPLES ((unsigned long long)XT_HYPER_SUPERS * XT_SUPER_SAMPLES)
 #define XT_MAX_CAND 4                                          // candidate binades of a multi tile
 #define XT_KBIAS 1100                                          // tile code: k + XT_KBIAS in bits 0-11 ...
 #define XT_CODE_NC(c) (((c) >> 12) & 7)                        // ... candidates in bits 12-14 (0 = none) ...
 #define XT_CODE_LITERAL 0x8000                                 // ... bit 15: summed literally, e0 = exit state ...
 #define XT_CODE_SLOT(c) ((unsigned)(c) >> 16)                  // ... bits 16-31: slot in the multi log
 #define XT_CODE_K(c) (((c) & 0xfff) - XT_KBIAS)
-#define XT_MAX_ITEMS 224                                       // chain items per shard
-#define XT_MAX_CROSS 48                                        // binade crossings per shard (a double has 2046 binades;
-                                                               // a shard of 2^36 samples passes < 40 above its first tile)
+#define XT_MAX_CROSS 44                                        // super-tiles per shard in which the running sum changes binade
 
 struct PaprTileRun { double e0, e1; };                         // increments for an even / odd entry state
 
@@ -140,10 +140,13 @@ struct PaprExactArgs {
 // what the chain of one shard boils down to: a short list of items applied in order to the running sum
 enum { XT_IT_SEG = 1, XT_IT_LIT = 2, XT_IT_ABS = 3 };
 struct PaprChainItem {
-    int type;       // SEG: a run (d[0], d[1]) valid in binade k; LIT: XT_RUN powers added literally, ending in binade k;
-    int k;          // ABS: the running sum becomes d[0] (valid for an entry state of exactly 0)
-    double d[XT_RUN];
+    int type;       // SEG: a run (e0, e1) valid in binade k; LIT: the one power e0 with which the running sum enters
+    int k;          //      binade k, added literally; ABS: the running sum becomes e0 (valid for an entry state of 0)
+    double e0, e1;
 };
+#define XT_MAX_ITEMS 96   // per shard, after runs of the same binade have been merged (a shard of 2^37 samples passes
+                          // < 40 binades above its first tile: one LIT and one or two SEG items each)
+#define XT_MAX_RAW 384    // ... before the merge
 enum { XT_OK = 0, XT_FALLBACK = 1, XT_NONFINITE = 2 };
 struct PaprChainList {
     int n;
@@ -161,7 +164,7 @@ struct PaprChainList {
 // latency-sized exchanges of a sharded analysis happen INSIDE the kernels that produce / consume
 // the values: publish to every peer's window, release-store the flag, acquire-poll the own window.
 #define PAPR_XCHG_MAX_RANKS 16
-enum { XK_PRE = 0, XK_STATS = 1, XK_COUNTS = 2 };
+enum { XK_PRE = 0, XK_STATS = 1, XK_COUNTS = 2, XK_CHAIN = 3, XK_KINDS = 4 };
 
 struct PaprXchgSlot {
     double pre[4];                                   // presample {sum, sum of squares, count, -}
@@ -169,10 +172,11 @@ struct PaprXchgSlot {
     // level counts + status word; two buffers used alternately (publication seq & 1): an analysis that
     // publishes counts twice (fused miss -> exact redo) never overwrites what a peer may still be summing
     unsigned long long counts[2][PAPR_MAX_LEVELS + 1];
+    PaprChainList chain;                             // what the shard's samples do to the running sum (papr_exact.cu)
 };
 
 struct PaprXchg {
-    unsigned long long flag[3][PAPR_XCHG_MAX_RANKS];
+    unsigned long long flag[XK_KINDS][PAPR_XCHG_MAX_RANKS];
     // abort[q] != 0: rank q gave up waiting (timeout) during the exchange with that sequence number of
     // kind XK_PRE; every later wait on any rank fails too, so all ranks report the same outcome
     unsigned long long abort[PAPR_XCHG_MAX_RANKS];
@@ -200,7 +204,8 @@ void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, unsigned l
                                  unsigned long long *status_word, const PaprChainList *chain /* or NULL */,
                                  int *chain_report /* {status, why} or NULL */, cudaStream_t s);
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
-                        PaprDevStats *merged, PaprDevLevels *lv, unsigned long long *status_word, cudaStream_t s);
+                        PaprDevStats *merged, PaprDevLevels *lv, unsigned long long *status_word, cudaStream_t s,
+                        const PaprChainList *chain = nullptr, int *chain_report = nullptr);
 void papr_launch_presample(const float *iq, unsigned long long nsamples, int stride, int grid,
                            double *cta_pre /* [grid*3] */, cudaStream_t s);
 void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s);
@@ -231,16 +236,20 @@ void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, flo
 void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
                                    unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,
-                                   unsigned long long seq, cudaStream_t s);
+                                   unsigned long long seq, cudaStream_t s, PaprDevStats *parts_out = nullptr);
+void papr_launch_xt_chain_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
+                            const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
+                            const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
+                            unsigned long long seq, cudaStream_t s);
 void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
                           unsigned long long seq, cudaStream_t s);
 int papr_scan_tma_configure(void);
 void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, const PaprScanArgs &a, const PaprExactArgs &x,
                           cudaStream_t s);
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles,
-                            const PaprTileRun *multi_tile, PaprSuperRec *super, int grid, cudaStream_t s);
-void papr_launch_xt_chain(const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
+                            const PaprTileRun *multi_tile, PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s);
+void papr_launch_xt_chain(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
                           const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
-                          PaprChainList *out /* two lists back to back: [0] result, [1] scratch */, cudaStream_t s);
+                          PaprChainList *out, cudaStream_t s);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

@@ -227,9 +227,10 @@ struct papr_engine {
     unsigned xt_multi_cap = 8192;
     PaprTileRun *d_xt_run = nullptr, *d_xt_multi = nullptr, *d_xt_multi_tile = nullptr;
     int *d_xt_code = nullptr;
-    PaprSuperRec *d_xt_super = nullptr;
+    PaprSuperRec *d_xt_super = nullptr, *d_xt_hyper = nullptr;
     unsigned *d_xt_multi_count = nullptr;
-    PaprChainList *d_xt_chain = nullptr; // [0] result, [1] scratch
+    PaprChainList *d_xt_chain = nullptr;
+    PaprDevStats *d_xt_parts = nullptr;  // sharded: every rank's pass-1 state, in rank order
     int xt_status = -1, xt_why = 0;      // of the last analysis (-1: the device chain did not run)
     // device work buffers
     int grid = 0;
@@ -260,7 +261,7 @@ struct papr_engine {
     PaprXchg *d_xchg = nullptr;
     PaprPeers peers = {};
     bool xchg_attached = false;
-    u64 xseq[3] = {0, 0, 0};
+    u64 xseq[XK_KINDS] = {0, 0, 0, 0};
     double xchg_timeout_s = 30.0; // how long a kernel waits for a peer's publication before every rank gives up
     // timing / accounting
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_scan[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -343,8 +344,9 @@ static int engine_init(papr_engine *e, int device)
     CU(cudaMalloc(&e->d_xt_multi, sizeof(PaprTileRun) * (size_t)e->xt_multi_cap * XT_MAX_CAND * XT_TILE_BATCHES));
     CU(cudaMalloc(&e->d_xt_multi_tile, sizeof(PaprTileRun) * (size_t)e->xt_multi_cap * XT_MAX_CAND));
     CU(cudaMalloc(&e->d_xt_multi_count, sizeof(unsigned)));
-    CU(cudaMalloc(&e->d_xt_chain, 2 * sizeof(PaprChainList)));
-    CU(cudaMemset(e->d_xt_chain, 0, 2 * sizeof(PaprChainList)));
+    CU(cudaMalloc(&e->d_xt_chain, sizeof(PaprChainList)));
+    CU(cudaMemset(e->d_xt_chain, 0, sizeof(PaprChainList)));
+    CU(cudaMalloc(&e->d_xt_parts, sizeof(PaprDevStats) * PAPR_XCHG_MAX_RANKS));
     {
         std::vector<double> t(4 * PAPR_MAX_LEVELS, INFINITY);
         papr_host_build_tables(0, kLevels1dB, &t[0], &t[2 * PAPR_MAX_LEVELS]);
@@ -389,8 +391,8 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (e->h_tile_run) cudaFreeHost(e->h_tile_run);
     if (e->h_tile_data) cudaFreeHost(e->h_tile_data);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
-    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super); cudaFree(e->d_xt_multi); cudaFree(e->d_xt_multi_tile);
-    cudaFree(e->d_xt_multi_count); cudaFree(e->d_xt_chain);
+    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super); cudaFree(e->d_xt_hyper); cudaFree(e->d_xt_multi); cudaFree(e->d_xt_multi_tile);
+    cudaFree(e->d_xt_multi_count); cudaFree(e->d_xt_chain); cudaFree(e->d_xt_parts);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_stage[0]) cudaFreeHost(e->h_stage[0]);
     for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
@@ -493,13 +495,14 @@ static TensorMapEncodeFn tensor_map_encoder()
 static int ensure_xt_buffers(papr_engine *e, u64 ntiles)
 {
     if (ntiles <= e->xt_tiles) return PAPR_OK;
-    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super);
-    e->d_xt_run = nullptr; e->d_xt_code = nullptr; e->d_xt_super = nullptr;
+    cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super); cudaFree(e->d_xt_hyper);
+    e->d_xt_run = nullptr; e->d_xt_code = nullptr; e->d_xt_super = nullptr; e->d_xt_hyper = nullptr;
     e->xt_tiles = 0;
     const u64 cap = std::max<u64>(ntiles, 1u << 16);
     CU(cudaMalloc(&e->d_xt_run, cap * sizeof(PaprTileRun)));
     CU(cudaMalloc(&e->d_xt_code, cap * sizeof(int)));
     CU(cudaMalloc(&e->d_xt_super, (cap / XT_SUPER_TILES + 1) * sizeof(PaprSuperRec)));
+    CU(cudaMalloc(&e->d_xt_hyper, (cap / XT_SUPER_TILES / XT_HYPER_SUPERS + 1) * sizeof(PaprSuperRec)));
     e->xt_tiles = cap;
     return PAPR_OK;
 }
@@ -553,9 +556,10 @@ static int enqueue_xt_chain(papr_engine *e, const float *d_iq, u64 n)
 {
     const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
     const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
-    papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super,
-                           (int)std::min<unsigned>((nsuper + 7) / 8, (unsigned)e->num_sms * 8), e->stream);
-    papr_launch_xt_chain(e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles, d_iq, n,
+    const unsigned nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
+    papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super, e->d_xt_hyper,
+                           (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
+    papr_launch_xt_chain(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles, d_iq, n,
                          e->d_xt_chain, e->stream);
     e->launches += 2;
     CU(cudaGetLastError());
@@ -1329,11 +1333,31 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
                             ++e->xseq[XK_PRE], e->stream);
     papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 3;
-    if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
-    papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                  &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
-                                  ++e->xseq[XK_STATS], e->stream);
-    e->launches += 1;
+    // the sequential sum inside the sweep: all ranks must agree on taking this path (same n is not required, the
+    // tunable and the minimum size are): every rank then runs the chain exchange
+    const bool chained = xt_applicable(e, n);
+    e->xt_status = -1;
+    if (chained) {
+        if ((rc = enqueue_scan_tma(e, d_iq, n, first, true))) return rc;
+        const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
+        const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES, nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
+        papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super, e->d_xt_hyper,
+                               (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
+        papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
+                                      &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
+                                      ++e->xseq[XK_STATS], e->stream, e->d_xt_parts);
+        papr_launch_xt_chain_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
+                               d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], e->stream);
+        papr_launch_levels(e->d_xt_parts, e->peers.world, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
+                           &e->d_out->counts[PAPR_MAX_LEVELS], e->stream, e->d_xt_chain, e->d_out->chain);
+        e->launches += 4;
+    } else {
+        if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
+        papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
+                                      &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
+                                      ++e->xseq[XK_STATS], e->stream);
+        e->launches += 1;
+    }
     if ((rc = enqueue_resolve(e))) return rc;
     papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
     e->launches += 1;
@@ -1342,6 +1366,11 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     CU(cudaStreamSynchronize(e->stream));
     if (e->h_out->o.plan.pad) return fail(e, PAPR_ERR_INTERNAL, "peer exchange timed out (a rank did not take part)");
     stats_to_host(e->h_out->o.merged, &out->stats);
+    if (chained) { // identical on every rank: all of them walked the same lists
+        e->xt_status = e->h_out->o.chain[0];
+        e->xt_why = e->h_out->o.chain[1];
+        out->sum_path = e->xt_status == XT_OK ? 1u : e->xt_status == XT_FALLBACK ? (2u | ((unsigned)e->xt_why << 8)) : 0u;
+    }
     // merged stats and the summed status word are identical on every rank, so every rank takes the
     // same branch here: thresholds outside the predicted windows somewhere -> exact pass everywhere
     if (collect(e, graph, out, true)) {

@@ -17,8 +17,10 @@
 // Everything is verified while it is applied (state inside the assumed binade before and after each run);
 // a failed check only ever sends the analysis to the slower two-sweep emulation, never to a wrong sum.
 #include <cuda.h>
+#include <cstdio>
 
 #include "papr_scan_common.cuh"
+#include "papr_xchg.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -437,52 +439,93 @@ __device__ __forceinline__ PaprTileRun xt_warp_compose(PaprTileRun r, int k)
     return r;
 }
 
-// one warp per super-tile, one lane per tile: for every binade that ALL its tiles have a run for, the
-// ordered composition of the 32 runs
-__global__ void __launch_bounds__(256) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
-                                                              unsigned ntiles, const PaprTileRun *multi_tile,
-                                                              PaprSuperRec *super)
+// One CTA per hyper-tile (32 super-tiles = 1024 tiles), one warp per super-tile, one lane per tile: for every
+// binade that ALL tiles of the super-tile have a run for, the ordered composition of the 32 runs; then warp 0
+// composes the 32 super-tile records the same way into the hyper-tile's record.
+__device__ __forceinline__ PaprTileRun xt_pick(const PaprSuperRec &r, int k) // k inside [r.k_lo, r.k_lo + r.nc)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
-    for (unsigned st = gw; st < nsuper; st += nw) {
-        const unsigned t = st * XT_SUPER_TILES + lane;
-        const bool have = t < ntiles;
-        const int code = have ? tile_code[t] : 0;
-        PaprTileRun run;
-        run.e0 = run.e1 = 0.0;
-        if (have) run = tile_run[t];
-        const int nc = have ? XT_CODE_NC(code) : 0, K = XT_CODE_K(code);
-        const double asum = run.e0;
-        // candidate binades of this tile; an all-zero tile (or none at all) is the identity in every binade
-        const bool ident = !have || (!(code & XT_CODE_LITERAL) && asum == 0.0);
-        int lo = ident ? -5000 : (nc >= 1 ? K : 5000), hi = ident ? 5000 : (nc >= 1 ? K + nc - 1 : -5000);
-        lo = __reduce_max_sync(FULL, lo);
-        hi = __reduce_min_sync(FULL, hi);
-        const int ncs = lo == -5000 ? 0 : max(0, min(hi - lo + 1, XT_SUPER_CAND)); // all identity: nothing to record
-        PaprSuperRec s;
-        s.k_lo = lo; s.nc = ncs;
+    PaprTileRun o = r.r[0];
 #pragma unroll
-        for (int cd = 0; cd < XT_SUPER_CAND; ++cd) {
-            s.r[cd].e0 = s.r[cd].e1 = 0.0;
-            if (cd < ncs) {
-                const int k = lo + cd;
-                PaprTileRun r;
-                r.e0 = r.e1 = 0.0;
-                if (!ident) r = nc == 1 ? run : multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (k - K)];
-                s.r[cd] = xt_warp_compose(r, k);
+    for (int cd = 1; cd < XT_SUPER_CAND; ++cd)
+        if (cd == k - r.k_lo) o = r.r[cd];
+    return o;
+}
+
+__global__ void __launch_bounds__(1024) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
+                                                               unsigned ntiles, const PaprTileRun *multi_tile,
+                                                               PaprSuperRec *super, PaprSuperRec *hyper)
+{
+    __shared__ PaprSuperRec s_rec[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
+    const unsigned nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
+    for (unsigned hy = blockIdx.x; hy < nhyper; hy += gridDim.x) {
+        const unsigned st = hy * XT_HYPER_SUPERS + warp;
+        {
+            const unsigned t = st * XT_SUPER_TILES + lane;
+            const bool have = st < nsuper && t < ntiles;
+            const int code = have ? tile_code[t] : 0;
+            PaprTileRun run;
+            run.e0 = run.e1 = 0.0;
+            if (have) run = tile_run[t];
+            const int nc = have ? XT_CODE_NC(code) : 0, K = XT_CODE_K(code);
+            const double asum = run.e0;
+            // candidate binades of this tile; an all-zero tile (or none at all) is the identity in every binade
+            const bool ident = !have || (!(code & XT_CODE_LITERAL) && asum == 0.0);
+            int lo = ident ? -5000 : (nc >= 1 ? K : 5000), hi = ident ? 5000 : (nc >= 1 ? K + nc - 1 : -5000);
+            lo = __reduce_max_sync(FULL, lo);
+            hi = __reduce_min_sync(FULL, hi);
+            const int ncs = lo == -5000 ? 0 : max(0, min(hi - lo + 1, XT_SUPER_CAND)); // all identity: nothing to record
+            PaprSuperRec s;
+            s.k_lo = lo; s.nc = ncs;
+#pragma unroll
+            for (int cd = 0; cd < XT_SUPER_CAND; ++cd) {
+                s.r[cd].e0 = s.r[cd].e1 = 0.0;
+                if (cd < ncs) {
+                    const int k = lo + cd;
+                    PaprTileRun r;
+                    r.e0 = r.e1 = 0.0;
+                    if (!ident) r = nc == 1 ? run : multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (k - K)];
+                    s.r[cd] = xt_warp_compose(r, k);
+                }
+            }
+            s.asum = warp_sum_fixed(asum);
+            if (lane == 0) {
+                if (st < nsuper) super[st] = s;
+                s_rec[warp] = s;
             }
         }
-        s.asum = warp_sum_fixed(asum);
-        if (lane == 0) super[st] = s;
+        __syncthreads();
+        if (warp == 0) { // the same one level up: lane = super-tile
+            const PaprSuperRec me = s_rec[lane];
+            const bool ident = me.asum == 0.0 && me.nc == 0; // (only zeros, or beyond the end)
+            int lo = ident ? -5000 : (me.nc >= 1 ? me.k_lo : 5000), hi = ident ? 5000 : (me.nc >= 1 ? me.k_lo + me.nc - 1 : -5000);
+            lo = __reduce_max_sync(FULL, lo);
+            hi = __reduce_min_sync(FULL, hi);
+            const int ncs = lo == -5000 ? 0 : max(0, min(hi - lo + 1, XT_SUPER_CAND));
+            PaprSuperRec h;
+            h.k_lo = lo; h.nc = ncs;
+#pragma unroll
+            for (int cd = 0; cd < XT_SUPER_CAND; ++cd) {
+                h.r[cd].e0 = h.r[cd].e1 = 0.0;
+                if (cd < ncs) {
+                    PaprTileRun r;
+                    r.e0 = r.e1 = 0.0;
+                    if (!ident) r = xt_pick(me, lo + cd);
+                    h.r[cd] = xt_warp_compose(r, lo + cd);
+                }
+            }
+            h.asum = warp_sum_fixed(me.asum);
+            if (lane == 0) hyper[hy] = h;
+        }
+        __syncthreads();
     }
 }
 
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi_tile,
-                            PaprSuperRec *super, int grid, cudaStream_t s)
+                            PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s)
 {
-    papr_xt_compose_kernel<<<grid, 256, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super);
+    papr_xt_compose_kernel<<<grid, 1024, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super, hyper);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,6 +538,8 @@ enum { // PaprChainList.why
 };
 
 struct XtCtx {
+    const PaprSuperRec *hyper;     // [nhyper] 32 super-tiles each
+    unsigned nhyper;
     const PaprSuperRec *super;
     const PaprTileRun *tile_run;
     const int *tile_code;
@@ -503,19 +548,6 @@ struct XtCtx {
     const float *iq;               // the shard (for the 8 + 248 samples around each crossing)
     unsigned long long nsamples;
 };
-
-// the run of tile t under binade k; false if the tile offers no such candidate
-__device__ __forceinline__ bool xt_tile_rec(const XtCtx &c, unsigned t, int k, PaprTileRun *out)
-{
-    out->e0 = out->e1 = 0.0;
-    if (t >= c.ntiles) return true;
-    const int code = c.tile_code[t], nc = XT_CODE_NC(code), K = XT_CODE_K(code);
-    if (nc == 1 && K == k) { *out = c.tile_run[t]; return true; }
-    if (nc > 1 && k >= K && k < K + nc) { *out = c.multi_tile[(size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (k - K)]; return true; }
-    // an all-zero tile is the identity in any binade
-    if (!(code & XT_CODE_LITERAL) && c.tile_run[t].e0 == 0.0) return true;
-    return false;
-}
 
 __device__ __forceinline__ double xt_warp_excl_scan(double v, int lane, double *total)
 {
@@ -529,28 +561,25 @@ __device__ __forceinline__ double xt_warp_excl_scan(double v, int lane, double *
     return inc - v; // exclusive (approximate sums only)
 }
 
-struct XtItemKey { unsigned long long pos; }; // shard-local sample index at which the item starts (sort key)
-
-// thread 0 of the CTA: apply the items in order.  Returns the status.
+// thread 0 of the CTA: apply a shard's items (in shared or global memory) in order.  Returns the status.
 __device__ int xt_walk(const PaprChainItem *item, int n, double *state, int *why)
 {
     double s = *state;
     for (int i = 0; i < n; ++i) {
-        const PaprChainItem &it = item[i];
+        const PaprChainItem it = item[i];
         if (it.type == XT_IT_SEG) {
-            if (it.d[0] == 0.0 && it.d[1] == 0.0) continue; // nothing but zeros: the identity in any binade
+            if (it.e0 == 0.0 && it.e1 == 0.0) continue; // nothing but zeros: the identity in any binade
             if (xt_expo(s) != it.k) { *why = XW_WALK_BINADE; return XT_FALLBACK; }
-            const double inc = xt_lsb(s) ? it.d[1] : it.d[0];
+            const double inc = xt_lsb(s) ? it.e1 : it.e0;
             const double s2 = __dadd_rn(s, inc); // whole ulps on both sides: exact while it stays in the binade
             if (!(inc >= 0.0) || !(s2 < xt_base(it.k + 1, 0))) { *why = XW_WALK_OVERFLOW; return XT_FALLBACK; }
             s = s2;
         } else if (it.type == XT_IT_LIT) {
-#pragma unroll
-            for (int j = 0; j < XT_RUN; ++j) s = __dadd_rn(s, it.d[j]); // papr.c:104 as written
+            s = __dadd_rn(s, it.e0); // papr.c:104 as written: the add that carries the sum into the next binade
             if (xt_expo(s) != it.k) { *why = XW_WALK_LITERAL; return XT_FALLBACK; }
         } else {
             if (s != 0.0) { *why = XW_WALK_ABS; return XT_FALLBACK; }
-            s = it.d[0];
+            s = it.e0;
         }
     }
     *state = s;
@@ -560,41 +589,81 @@ __device__ int xt_walk(const PaprChainItem *item, int n, double *state, int *why
 #define XT_CHAIN_T 1024
 #define XT_MAX_XTILES 64
 
-// Builds the item list of this shard: out->item[0..n) in file order.  pre_approx = approximate running sum
-// before the shard (0 for the first); literal tiles produce an ABS item.
-__device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList *out)
+// this lane's tile inside a crossing super-tile, loaded once
+struct XtTile {
+    int code;
+    PaprTileRun run;             // single tiles: the run; otherwise e0 = approximate sum
+    PaprTileRun cand[XT_MAX_CAND]; // multi tiles: the run per candidate
+};
+
+__device__ __forceinline__ bool xt_tile_pick(const XtTile &t, bool have, int k, PaprTileRun *out)
+{
+    out->e0 = out->e1 = 0.0;
+    if (!have) return true;
+    const int nc = XT_CODE_NC(t.code), K = XT_CODE_K(t.code);
+    if (nc == 1 && K == k) { *out = t.run; return true; }
+    if (nc > 1 && k >= K && k < K + nc) {
+#pragma unroll
+        for (int cd = 0; cd < XT_MAX_CAND; ++cd)
+            if (cd == k - K) *out = t.cand[cd];
+        return true;
+    }
+    return !(t.code & XT_CODE_LITERAL) && t.run.e0 == 0.0; // an all-zero tile is the identity in any binade
+}
+
+// the merged chain of a shard, in shared memory while it is built and walked
+struct XtShared {
+    PaprChainItem item[XT_MAX_ITEMS];
+    int n;
+};
+
+// Builds the item list of this shard (sh->item[0..n) in file order, runs of the same binade merged; copied to
+// *out as well).  pre_approx = approximate running sum before the shard (0 for the first).  All threads
+// return the status.
+__device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList *out, XtShared *sh)
 {
     __shared__ double s_scan[XT_CHAIN_T];
     __shared__ PaprTileRun s_piece[XT_CHAIN_T + XT_MAX_CROSS + 1];
     __shared__ short s_piece_k[XT_CHAIN_T + XT_MAX_CROSS + 1]; // the binade each piece was composed for
-    __shared__ unsigned s_xs[XT_MAX_CROSS];    // crossing super-tiles, ascending
-    __shared__ double s_xp[XT_MAX_CROSS];      // approximate running sum at their start
+    __shared__ unsigned s_xh[XT_MAX_CROSS];    // crossing hyper-tiles, ascending
+    __shared__ double s_xhp[XT_MAX_CROSS];     // approximate running sum at their start
+    __shared__ unsigned s_xs[XT_MAX_CROSS];    // crossing super-tiles
+    __shared__ double s_xp[XT_MAX_CROSS];
     __shared__ unsigned s_xt[XT_MAX_XTILES];   // crossing tiles
     __shared__ double s_xtp[XT_MAX_XTILES];
-    __shared__ unsigned long long s_key[XT_MAX_ITEMS];
-    __shared__ int s_nx, s_nxt, s_nitems, s_status, s_why;
+    __shared__ unsigned long long s_key[XT_MAX_RAW];
+    __shared__ double s_re0[XT_MAX_RAW], s_re1[XT_MAX_RAW]; // the raw items
+    __shared__ short s_rk[XT_MAX_RAW];
+    __shared__ char s_rtype[XT_MAX_RAW];
+    __shared__ short s_order[XT_MAX_RAW];      // raw index of the r-th item in file order
+    __shared__ short s_gstart[XT_MAX_ITEMS];
+    __shared__ short s_ord2[XT_MAX_RAW];       // ... without the identities
+    __shared__ int s_woff[XT_MAX_RAW / 32 + 1];
+    __shared__ int s_nxh, s_nx, s_nxt, s_nraw, s_status, s_why, s_ngroups, s_ncomp;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    PaprChainItem *stage = out->item; // staged unsorted in place? no: sorted copy needs a second buffer -> see below
-    if (t == 0) { s_nx = 0; s_nxt = 0; s_nitems = 0; s_status = XT_OK; s_why = XW_NONE; }
+#ifdef XT_TIMING
+    unsigned long long tm[12];
+    int tmi = 0;
+#define XT_MARK() do { if (t == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tm[tmi])); ++tmi; } } while (0)
+#else
+#define XT_MARK() do { } while (0)
+#endif
+    XT_MARK();
+    if (t == 0) { s_nxh = 0; s_nx = 0; s_nxt = 0; s_nraw = 0; s_status = XT_OK; s_why = XW_NONE; s_ngroups = 0; s_ncomp = 0; }
     __syncthreads();
     auto fail = [&](int why) { if (atomicCAS(&s_status, XT_OK, XT_FALLBACK) == XT_OK) s_why = why; };
-    // item staging area: the second half of out->item is not needed until the sort, so items are staged in a
-    // separate global scratch that follows the list (the caller allocates two lists back to back)
-    PaprChainItem *scratch = (out + 1)->item;
-    auto emit = [&](int type, int k, unsigned long long pos, const double *d, int nd) {
-        const int i = atomicAdd(&s_nitems, 1);
-        if (i >= XT_MAX_ITEMS) { fail(XW_TOO_MANY_ITEMS); return; }
-        scratch[i].type = type;
-        scratch[i].k = k;
-        for (int j = 0; j < XT_RUN; ++j) scratch[i].d[j] = j < nd ? d[j] : 0.0;
-        s_key[i] = pos;
+    auto emit = [&](int type, int k, unsigned long long pos, double e0, double e1) -> int {
+        const int i = atomicAdd(&s_nraw, 1);
+        if (i >= XT_MAX_RAW) { fail(XW_TOO_MANY_ITEMS); return -1; }
+        s_key[i] = pos; s_rtype[i] = (char)type; s_rk[i] = (short)k; s_re0[i] = e0; s_re1[i] = e1;
+        return i;
     };
 
-    // ---- 1. approximate running sum at every super-tile (block scan of chunk sums)
-    const unsigned m = (c.nsuper + XT_CHAIN_T - 1) / XT_CHAIN_T;
-    const unsigned lo = min(c.nsuper, (unsigned)t * m), hi = min(c.nsuper, lo + m);
+    // ---- 1. approximate running sum at every hyper-tile (block scan of chunk sums)
+    const unsigned m = (c.nhyper + XT_CHAIN_T - 1) / XT_CHAIN_T;
+    const unsigned lo = min(c.nhyper, (unsigned)t * m), hi = min(c.nhyper, lo + m);
     double chunk = 0.0;
-    for (unsigned i = lo; i < hi; ++i) chunk += c.super[i].asum;
+    for (unsigned i = lo; i < hi; ++i) chunk += c.hyper[i].asum;
     s_scan[t] = chunk;
     __syncthreads();
     for (int o = 1; o < XT_CHAIN_T; o <<= 1) {
@@ -606,50 +675,51 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
     const double total = pre_approx + s_scan[XT_CHAIN_T - 1];
     if (t == 0) out->approx = s_scan[XT_CHAIN_T - 1];
     if (!isfinite(total)) { // NaN / Inf among the powers: so is the reference's sum, nothing to emulate
-        if (t == 0) { out->n = 0; out->status = XT_NONFINITE; out->why = XW_NONE; }
+        if (t == 0) { out->n = 0; out->status = XT_NONFINITE; out->why = XW_NONE; sh->n = 0; }
         __syncthreads();
-        return;
+        return XT_NONFINITE;
     }
     const double p_chunk = pre_approx + (s_scan[t] - chunk);
+    XT_MARK(); // 1: prefix done
 
-    // ---- 2. super-tiles inside which the running sum changes binade (or starts from zero)
+    // ---- 2. hyper-tiles inside which the running sum changes binade (or starts from zero)
     {
         double p = p_chunk;
         for (unsigned i = lo; i < hi; ++i) {
-            const double pn = p + c.super[i].asum;
+            const double pn = p + c.hyper[i].asum;
             if (xt_expo(p) != xt_expo(pn)) {
-                const int j = atomicAdd(&s_nx, 1);
-                if (j < XT_MAX_CROSS) { s_xs[j] = i; s_xp[j] = p; } else fail(XW_TOO_MANY_CROSSINGS);
+                const int j = atomicAdd(&s_nxh, 1);
+                if (j < XT_MAX_CROSS) { s_xh[j] = i; s_xhp[j] = p; } else fail(XW_TOO_MANY_CROSSINGS);
             }
             p = pn;
         }
     }
     __syncthreads();
-    const int nx = min(s_nx, XT_MAX_CROSS);
-    if (t == 0) // ascending (<= 48 entries)
-        for (int i = 1; i < nx; ++i) {
-            const unsigned v = s_xs[i];
-            const double pv = s_xp[i];
+    const int nxh = min(s_nxh, XT_MAX_CROSS);
+    if (t == 0) // ascending (<= 44 entries)
+        for (int i = 1; i < nxh; ++i) {
+            const unsigned v = s_xh[i];
+            const double pv = s_xhp[i];
             int j = i - 1;
-            while (j >= 0 && s_xs[j] > v) { s_xs[j + 1] = s_xs[j]; s_xp[j + 1] = s_xp[j]; --j; }
-            s_xs[j + 1] = v; s_xp[j + 1] = pv;
+            while (j >= 0 && s_xh[j] > v) { s_xh[j + 1] = s_xh[j]; s_xhp[j + 1] = s_xhp[j]; --j; }
+            s_xh[j + 1] = v; s_xhp[j + 1] = pv;
         }
     __syncthreads();
 
-    // ---- 3. the stretches of super-tiles between them: every thread composes its chunk, cut at the crossing
-    //         super-tiles; piece index t + (crossings before it) puts all pieces in file order, and the pieces
+    // ---- 3. the stretches of hyper-tiles between them: every thread composes its chunk, cut at the crossing
+    //         hyper-tiles; piece index t + (crossings before it) puts all pieces in file order, and the pieces
     //         of stretch number s are exactly those with index - thread == s
     {
-        int xb = 0; // crossing super-tiles before this chunk
-        while (xb < nx && s_xs[xb] < lo) ++xb;
+        int xb = 0; // crossing hyper-tiles before this chunk
+        while (xb < nxh && s_xh[xb] < lo) ++xb;
         int seg = xb;
         double p = p_chunk;
         PaprTileRun cur;
         cur.e0 = cur.e1 = 0.0;
         int k = xt_expo(p);
         for (unsigned i = lo; i < hi; ++i) {
-            const PaprSuperRec sr = c.super[i];
-            if (seg < nx && s_xs[seg] == i) {
+            const PaprSuperRec sr = c.hyper[i];
+            if (seg < nxh && s_xh[seg] == i) {
                 s_piece[t + seg] = cur;
                 s_piece_k[t + seg] = (short)k;
                 cur.e0 = cur.e1 = 0.0;
@@ -658,28 +728,22 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
                 k = xt_expo(p);
                 continue;
             }
-            if (sr.nc > 0 && k >= sr.k_lo && k < sr.k_lo + sr.nc) {
-                cur = xt_compose(cur, sr.r[k - sr.k_lo], k);
-            } else if (!(sr.asum == 0.0)) { // (nothing but zeros: the identity in any binade)
-                fail(XW_SUPER_MISPREDICTED);
-            }
+            if (sr.nc > 0 && k >= sr.k_lo && k < sr.k_lo + sr.nc) cur = xt_compose(cur, xt_pick(sr, k), k);
+            else if (!(sr.asum == 0.0)) fail(XW_SUPER_MISPREDICTED); // (nothing but zeros: the identity in any binade)
             p += sr.asum;
         }
         s_piece[t + seg] = cur;
         s_piece_k[t + seg] = (short)k;
     }
     __syncthreads();
-    for (int s = warp; s <= nx; s += XT_CHAIN_T / 32) { // one warp per stretch
-        const unsigned a = s == 0 ? 0u : s_xs[s - 1] + 1u, b = s == nx ? c.nsuper : s_xs[s];
+    for (int s = warp; s <= nxh; s += XT_CHAIN_T / 32) { // one warp per stretch
+        const unsigned a = s == 0 ? 0u : s_xh[s - 1] + 1u, b = s == nxh ? c.nhyper : s_xh[s];
         if (a >= b) continue;
         // binade of the stretch: the running sum at its start
-        double p0;
-        if (s == 0) p0 = pre_approx;
-        else p0 = s_xp[s - 1] + c.super[s_xs[s - 1]].asum;
+        const double p0 = s == 0 ? pre_approx : s_xhp[s - 1] + c.hyper[s_xh[s - 1]].asum;
         const int k = xt_expo(p0);
         const unsigned ta = a / m, tb = (b - 1) / m;
-        // lanes take contiguous thread ranges
-        const unsigned cnt = tb - ta + 1, per = (cnt + 31) / 32;
+        const unsigned cnt = tb - ta + 1, per = (cnt + 31) / 32; // lanes take contiguous thread ranges
         PaprTileRun r;
         r.e0 = r.e1 = 0.0;
         for (unsigned q = 0; q < per; ++q) {
@@ -693,59 +757,101 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             }
         }
         r = xt_warp_compose(r, k);
-        if (lane == 0) {
-            const double d[2] = {r.e0, r.e1};
-            emit(XT_IT_SEG, k, (unsigned long long)a * XT_SUPER_SAMPLES, d, 2);
+        if (lane == 0) emit(XT_IT_SEG, k, (unsigned long long)a * XT_HYPER_SAMPLES, r.e0, r.e1);
+    }
+
+    __syncthreads();
+    XT_MARK(); // 2: stretches of hyper-tiles done
+    // ---- 3b. inside every crossing hyper-tile: the super-tiles in which it happens, the stretches between
+    for (int x = warp; x < nxh; x += XT_CHAIN_T / 32) {
+        const unsigned hy = s_xh[x], st = hy * XT_HYPER_SUPERS + lane;
+        const bool have = st < c.nsuper;
+        PaprSuperRec me;
+        me.asum = 0.0; me.k_lo = 0; me.nc = 0;
+#pragma unroll
+        for (int cd = 0; cd < XT_SUPER_CAND; ++cd) me.r[cd].e0 = me.r[cd].e1 = 0.0;
+        if (have) me = c.super[st];
+        double tot;
+        const double pl = s_xhp[x] + xt_warp_excl_scan(me.asum, lane, &tot), pa = pl + me.asum;
+        const bool cross = have && xt_expo(pl) != xt_expo(pa);
+        if (cross) {
+            const int j = atomicAdd(&s_nx, 1);
+            if (j < XT_MAX_CROSS) { s_xs[j] = st; s_xp[j] = pl; } else fail(XW_TOO_MANY_CROSSINGS);
+        }
+        const unsigned bnd = __ballot_sync(FULL, cross);
+        int a = 0;
+        while (a < 32) {
+            const unsigned rest = bnd >> a;
+            const int b = rest ? a + (__ffs(rest) - 1) : 32; // stretch = lanes [a, b)
+            if (b > a) {
+                const int k = xt_expo(__shfl_sync(FULL, pl, a)); // binade at its start
+                PaprTileRun r;
+                r.e0 = r.e1 = 0.0;
+                bool ok = true;
+                if (have && lane >= a && lane < b) {
+                    if (me.nc > 0 && k >= me.k_lo && k < me.k_lo + me.nc) r = xt_pick(me, k);
+                    else ok = me.asum == 0.0;
+                }
+                if (!__all_sync(FULL, ok)) { if (lane == 0) fail(XW_SUPER_MISPREDICTED); }
+                r = xt_warp_compose(r, k);
+                if (lane == 0) emit(XT_IT_SEG, k, (unsigned long long)(hy * XT_HYPER_SUPERS + a) * XT_SUPER_SAMPLES, r.e0, r.e1);
+            }
+            a = b + 1;
         }
     }
+    __syncthreads();
+    const int nx = min(s_nx, XT_MAX_CROSS);
+    XT_MARK(); // 3: 3b done
 
     // ---- 4. inside every crossing super-tile: the tiles in which it happens, and the stretches of tiles between
     for (int x = warp; x < nx; x += XT_CHAIN_T / 32) {
         const unsigned st = s_xs[x], tl = st * XT_SUPER_TILES + lane;
         const bool have = tl < c.ntiles;
-        const int code = have ? c.tile_code[tl] : 0;
-        const double asum = have ? c.tile_run[tl].e0 : 0.0;
+        XtTile tt;
+        tt.code = have ? c.tile_code[tl] : 0;
+        tt.run.e0 = tt.run.e1 = 0.0;
+        if (have) tt.run = c.tile_run[tl];
+#pragma unroll
+        for (int cd = 0; cd < XT_MAX_CAND; ++cd) {
+            tt.cand[cd].e0 = tt.cand[cd].e1 = 0.0;
+            if (have && cd < XT_CODE_NC(tt.code) && XT_CODE_NC(tt.code) > 1)
+                tt.cand[cd] = c.multi_tile[(size_t)XT_CODE_SLOT(tt.code) * XT_MAX_CAND + cd];
+        }
+        const double asum = tt.run.e0;
         double tot;
         const double pl = s_xp[x] + xt_warp_excl_scan(asum, lane, &tot), pa = pl + asum;
-        const bool lit = have && (code & XT_CODE_LITERAL);
+        const bool lit = have && (tt.code & XT_CODE_LITERAL);
         const bool cross = have && !lit && xt_expo(pl) != xt_expo(pa);
         if (cross && xt_expo(pa) != xt_expo(pl) + 1) fail(xt_expo(pl) <= -4000 ? XW_START_UNKNOWN : XW_TWO_CROSSINGS_IN_TILE);
         if (lit) {
             if (pl != 0.0) fail(XW_WALK_ABS);
-            const double d[1] = {c.tile_run[tl].e0};
-            emit(XT_IT_ABS, 0, (unsigned long long)tl * XT_TILE_SAMPLES, d, 1);
+            emit(XT_IT_ABS, 0, (unsigned long long)tl * XT_TILE_SAMPLES, tt.run.e0, 0.0);
         }
         if (cross) {
             const int j = atomicAdd(&s_nxt, 1);
             if (j < XT_MAX_XTILES) { s_xt[j] = tl; s_xtp[j] = pl; } else fail(XW_TOO_MANY_CROSSINGS);
         }
         // stretches of ordinary tiles between the boundaries (crossing / literal tiles)
-        unsigned bnd = __ballot_sync(FULL, cross || lit);
+        const unsigned bnd = __ballot_sync(FULL, cross || lit);
         int a = 0;
         while (a < 32) {
             const unsigned rest = bnd >> a;
             const int b = rest ? a + (__ffs(rest) - 1) : 32; // stretch = lanes [a, b)
             if (b > a) {
-                // binade at its start
-                const double pst = __shfl_sync(FULL, pl, a);
-                const int k = xt_expo(pst);
+                const int k = xt_expo(__shfl_sync(FULL, pl, a)); // binade at its start
                 PaprTileRun r;
-                r.e0 = r.e1 = 0.0;
-                bool ok = true;
-                if (lane >= a && lane < b) ok = xt_tile_rec(c, tl, k, &r);
+                const bool ok = xt_tile_pick(tt, have && lane >= a && lane < b, k, &r);
                 if (!__all_sync(FULL, ok)) { if (lane == 0) fail(XW_TILE_NO_CANDIDATE); }
                 r = xt_warp_compose(r, k);
-                if (lane == 0) {
-                    const double d[2] = {r.e0, r.e1};
-                    emit(XT_IT_SEG, k, (unsigned long long)(st * XT_SUPER_TILES + a) * XT_TILE_SAMPLES, d, 2);
-                }
+                if (lane == 0) emit(XT_IT_SEG, k, (unsigned long long)(st * XT_SUPER_TILES + a) * XT_TILE_SAMPLES, r.e0, r.e1);
             }
             a = b + 1;
         }
     }
     __syncthreads();
 
-    // ---- 5. inside every crossing tile: the batch, then the 8 samples
+    XT_MARK(); // 4: tiles done
+    // ---- 5. inside every crossing tile: the batch, then the XT_RUN samples
     const int nxt = min(s_nxt, XT_MAX_XTILES);
     for (int x = warp; x < nxt; x += XT_CHAIN_T / 32) {
         const unsigned tl = s_xt[x];
@@ -764,6 +870,17 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
         const int bx = __ffs(xb) - 1;
         const double pbx = __shfl_sync(FULL, pl, bx);
         const unsigned long long tile_pos = (unsigned long long)tl * XT_TILE_SAMPLES;
+        // the crossing batch: this lane's XT_RUN samples (issued before the compositions below: HBM latency)
+        const unsigned long long s0 = tile_pos + (unsigned long long)bx * XT_BATCH_SAMPLES + (unsigned long long)XT_RUN * lane;
+        float v[XT_RUN];
+#pragma unroll
+        for (int j = 0; j < XT_RUN; ++j) {
+            v[j] = 0.f;
+            if (s0 + j < c.nsamples) {
+                const float2 h = *reinterpret_cast<const float2 *>(c.iq + 2 * (s0 + j));
+                v[j] = power_of(h.x, h.y);
+            }
+        }
         { // batches before: binade kb; after: ka
             PaprTileRun r = rb;
             if (lane >= bx) r.e0 = r.e1 = 0.0;
@@ -772,20 +889,8 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             if (lane <= bx || lane >= XT_TILE_BATCHES) q.e0 = q.e1 = 0.0;
             q = xt_warp_compose(q, ka);
             if (lane == 0) {
-                const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
-                emit(XT_IT_SEG, kb, tile_pos + 1, d, 2);                                  // after the tile-level stretch that ends here
-                emit(XT_IT_SEG, ka, tile_pos + (unsigned long long)(bx + 1) * XT_BATCH_SAMPLES, e, 2);
-            }
-        }
-        // the crossing batch: this lane's 8 samples, runs for both binades
-        const unsigned long long s0 = tile_pos + (unsigned long long)bx * XT_BATCH_SAMPLES + (unsigned long long)XT_RUN * lane;
-        double v[XT_RUN];
-#pragma unroll
-        for (int j = 0; j < XT_RUN; ++j) {
-            v[j] = 0.0;
-            if (s0 + j < c.nsamples) {
-                const float2 h = *reinterpret_cast<const float2 *>(c.iq + 2 * (s0 + j));
-                v[j] = (double)power_of(h.x, h.y);
+                emit(XT_IT_SEG, kb, tile_pos + 1, r.e0, r.e1); // after the tile-level stretch that ends here
+                emit(XT_IT_SEG, ka, tile_pos + (unsigned long long)(bx + 1) * XT_BATCH_SAMPLES, q.e0, q.e1);
             }
         }
         PaprTileRun lb, la;
@@ -793,8 +898,9 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             double a0 = xt_base(kb, 0), a1 = xt_base(kb, 1), b0 = xt_base(ka, 0), b1 = xt_base(ka, 1);
 #pragma unroll
             for (int j = 0; j < XT_RUN; ++j) {
-                a0 = __dadd_rn(a0, v[j]); a1 = __dadd_rn(a1, v[j]);
-                b0 = __dadd_rn(b0, v[j]); b1 = __dadd_rn(b1, v[j]);
+                const double d = (double)v[j];
+                a0 = __dadd_rn(a0, d); a1 = __dadd_rn(a1, d);
+                b0 = __dadd_rn(b0, d); b1 = __dadd_rn(b1, d);
             }
             lb.e0 = __dsub_rn(a0, xt_base(kb, 0)); lb.e1 = __dsub_rn(a1, xt_base(kb, 1));
             la.e0 = __dsub_rn(b0, xt_base(ka, 0)); la.e1 = __dsub_rn(b1, xt_base(ka, 1));
@@ -812,47 +918,215 @@ __device__ void xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainLis
             q = xt_warp_compose(q, ka);
             const unsigned long long bpos = tile_pos + (unsigned long long)bx * XT_BATCH_SAMPLES;
             if (lane == 0) {
-                const double d[2] = {r.e0, r.e1}, e[2] = {q.e0, q.e1};
-                emit(XT_IT_SEG, kb, bpos + 2, d, 2);
-                emit(XT_IT_SEG, ka, bpos + (unsigned long long)XT_RUN * (lx + 1), e, 2);
+                emit(XT_IT_SEG, kb, bpos + 2, r.e0, r.e1);
+                emit(XT_IT_SEG, ka, bpos + (unsigned long long)XT_RUN * (lx + 1), q.e0, q.e1);
             }
-            if (lane == lx) emit(XT_IT_LIT, ka, bpos + (unsigned long long)XT_RUN * lx + 3, v, XT_RUN);
+            if (lane == lx) {
+                // inside the run: the one sample whose add leaves binade kb is applied literally; the samples
+                // before it form a run in kb, those after it a run in ka (single-sample runs composed in order)
+                double q0 = ql;
+                int jx = -1;
+                PaprTileRun pre, post;
+                pre.e0 = pre.e1 = post.e0 = post.e1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < XT_RUN; ++j) {
+                    const double d = (double)v[j];
+                    const int kk = jx < 0 ? kb : ka;
+                    PaprTileRun one;
+                    one.e0 = __dsub_rn(__dadd_rn(xt_base(kk, 0), d), xt_base(kk, 0));
+                    one.e1 = __dsub_rn(__dadd_rn(xt_base(kk, 1), d), xt_base(kk, 1));
+                    if (jx < 0 && xt_expo(q0) != xt_expo(q0 + d)) jx = j;
+                    else if (jx < 0) pre = xt_compose(pre, one, kb);
+                    else post = xt_compose(post, one, ka);
+                    q0 += d;
+                }
+                const unsigned long long rpos = bpos + (unsigned long long)XT_RUN * lx;
+                if (jx < 0) fail(XW_LANE_NOT_FOUND);
+                else {
+                    double lit = 0.0;
+#pragma unroll
+                    for (int j = 0; j < XT_RUN; ++j)
+                        if (j == jx) lit = (double)v[j];
+                    emit(XT_IT_SEG, kb, rpos + 3, pre.e0, pre.e1);
+                    emit(XT_IT_LIT, ka, rpos + 4, lit, 0.0);
+                    emit(XT_IT_SEG, ka, rpos + 5, post.e0, post.e1);
+                }
+            }
         }
     }
+    __threadfence_block();
     __syncthreads();
 
-    // ---- 6. file order: rank every item by its key, scatter into the list
-    const int ni = min(s_nitems, XT_MAX_ITEMS);
-    for (int i = t; i < ni; i += XT_CHAIN_T) {
+    XT_MARK(); // 5: batches + lanes done
+    // ---- 6. file order: rank every item by its key
+    const int nr = min(s_nraw, XT_MAX_RAW);
+    for (int i = t; i < nr; i += XT_CHAIN_T) {
         const unsigned long long ki = s_key[i];
         int rank = 0;
-        for (int j = 0; j < ni; ++j) rank += (s_key[j] < ki) || (s_key[j] == ki && j < i);
-        out->item[rank] = scratch[i];
+        for (int j = 0; j < nr; ++j) rank += (s_key[j] < ki) || (s_key[j] == ki && j < i);
+        s_order[rank] = (short)i;
     }
-    if (t == 0) { out->n = ni; out->status = s_status; out->why = s_why; }
+    __syncthreads();
+    // ---- 7. identities dropped; runs of the same binade that follow each other become one item
+    {
+        // (a) compaction: position r (file order) -> position among the items that do something
+        const int i = t < nr ? s_order[t] : 0;
+        const bool keep = t < nr && !(s_rtype[i] == XT_IT_SEG && s_re0[i] == 0.0 && s_re1[i] == 0.0);
+        const unsigned kb = __ballot_sync(FULL, keep);
+        if (lane == 0 && warp <= XT_MAX_RAW / 32) s_woff[warp] = __popc(kb);
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int w = 0; w <= XT_MAX_RAW / 32; ++w) { const int c2 = s_woff[w]; s_woff[w] = acc; acc += c2; }
+            s_ncomp = acc;
+        }
+        __syncthreads();
+        if (keep) s_ord2[s_woff[warp] + __popc(kb & ((1u << lane) - 1u))] = (short)i;
+        __syncthreads();
+        // (b) group heads: an item starts a group unless it and its predecessor are runs of the same binade
+        const int nc2 = s_ncomp;
+        const int me = t < nc2 ? s_ord2[t] : 0, prev = (t > 0 && t < nc2) ? s_ord2[t - 1] : 0;
+        const bool head = t < nc2 && !(t > 0 && s_rtype[me] == XT_IT_SEG && s_rtype[prev] == XT_IT_SEG && s_rk[me] == s_rk[prev]);
+        const unsigned hb = __ballot_sync(FULL, head);
+        if (lane == 0 && warp <= XT_MAX_RAW / 32) s_woff[warp] = __popc(hb);
+        __syncthreads();
+        if (t == 0) {
+            int acc = 0;
+            for (int w = 0; w <= XT_MAX_RAW / 32; ++w) { const int c2 = s_woff[w]; s_woff[w] = acc; acc += c2; }
+            s_ngroups = acc;
+            if (acc > XT_MAX_ITEMS) fail(XW_TOO_MANY_ITEMS);
+        }
+        __syncthreads();
+        if (head) {
+            const int g = s_woff[warp] + __popc(hb & ((1u << lane) - 1u));
+            if (g < XT_MAX_ITEMS) s_gstart[g] = (short)t;
+        }
+        __syncthreads();
+    }
+    XT_MARK(); // 6: sorted + grouped
+    const int ng = min(s_ngroups, XT_MAX_ITEMS);
+    for (int g = t; g < ng; g += XT_CHAIN_T) {
+        const int q0 = s_gstart[g], q1 = g + 1 < ng ? s_gstart[g + 1] : s_ncomp;
+        const int i0 = s_ord2[q0];
+        PaprChainItem it;
+        it.type = s_rtype[i0]; it.k = s_rk[i0];
+        it.e0 = s_re0[i0]; it.e1 = s_re1[i0];
+        if (it.type == XT_IT_SEG) {
+            PaprTileRun r;
+            r.e0 = it.e0; r.e1 = it.e1;
+            for (int q = q0 + 1; q < q1; ++q) {
+                const int iq = s_ord2[q];
+                PaprTileRun b2;
+                b2.e0 = s_re0[iq]; b2.e1 = s_re1[iq];
+                r = xt_compose(r, b2, it.k);
+            }
+            it.e0 = r.e0; it.e1 = r.e1;
+        }
+        sh->item[g] = it;
+        out->item[g] = it; // a copy in global memory (other ranks walk it too in a sharded analysis)
+    }
+    if (t == 0) { sh->n = ng; out->n = ng; out->status = s_status; out->why = s_why; }
     __threadfence();
     __syncthreads();
+    XT_MARK(); // 7: merged + copied
+#ifdef XT_TIMING
+    if (t == 0) {
+        printf("xt chain ns: prefix %llu stretches %llu hyper %llu tiles %llu lanes %llu sort %llu merge %llu | raw %d items %d nxh %d nx %d nxt %d\n",
+               tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3], tm[5] - tm[4], tm[6] - tm[5], tm[7] - tm[6], nr, ng, nxh, nx, nxt);
+    }
+#endif
+    return s_status;
 }
 
 // single shard: prepare + walk
 __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_kernel(XtCtx c, PaprChainList *out)
 {
-    xt_chain_prepare(c, 0.0, out);
-    if (threadIdx.x == 0 && out->status == XT_OK) {
+    __shared__ XtShared sh;
+    const int st = xt_chain_prepare(c, 0.0, out, &sh);
+    if (threadIdx.x == 0 && st == XT_OK) {
         double s = 0.0;
         int why = XW_NONE;
-        out->status = xt_walk(out->item, out->n, &s, &why);
+#ifdef XT_TIMING
+        unsigned long long w0, w1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
+#endif
+        out->status = xt_walk(sh.item, sh.n, &s, &why);
+#ifdef XT_TIMING
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
+        printf("xt walk ns: %llu\n", w1 - w0);
+#endif
         out->why = why;
         out->exact = s;
     }
 }
 
-void papr_launch_xt_chain(const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
+void papr_launch_xt_chain(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
                           const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
                           PaprChainList *out, cudaStream_t s)
 {
     XtCtx c;
-    c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
+    c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
     c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
+    c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
     papr_xt_chain_kernel<<<1, XT_CHAIN_T, 0, s>>>(c, out);
+}
+
+// sharded (one process per GPU): every rank builds the list of its own shard - placing it after the lower
+// ranks' approximate sums, which the statistics exchange of this analysis has just delivered - publishes it to
+// every peer's window over NVLink, collects the others', and walks ALL lists in rank order from a running sum
+// of 0: the same work and the same verdict on every rank, no hand-over from GPU to GPU.
+__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_x_kernel(XtCtx c, PaprChainList *out, PaprPlan *plan,
+                                                                    PaprPeers pp, u64 seq)
+{
+    __shared__ XtShared sh;
+    __shared__ int s_st, s_why;
+    __shared__ double s_state;
+    double pre = 0.0;
+    for (int q = 0; q < pp.rank; ++q)
+        pre += __longlong_as_double((long long)ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats.sum)));
+    xt_chain_prepare(c, pre, out, &sh);
+    // header + the items in use
+    const int words = (int)((offsetof(PaprChainList, item) + sizeof(PaprChainItem) * (size_t)max(out->n, 0)) / 8);
+    xchg_publish(pp, XK_CHAIN, offsetof(PaprXchgSlot, chain), reinterpret_cast<const u64 *>(out), words, seq);
+    const bool ok = xchg_wait(pp, XK_CHAIN, seq);
+    if (threadIdx.x == 0) {
+        if (!ok) plan->pad = 1;
+        s_st = ok ? XT_OK : XT_FALLBACK;
+        s_why = XW_NONE;
+        s_state = 0.0;
+    }
+    __syncthreads();
+    for (int q = 0; q < pp.world; ++q) {
+        const PaprChainList *src = &pp.win[pp.rank]->slot[q].chain;
+        const int nq = min((int)ld_volatile(reinterpret_cast<const u64 *>(src)) & 0x7fffffff, XT_MAX_ITEMS); // {n, status}
+        const int stq = (int)(ld_volatile(reinterpret_cast<const u64 *>(src)) >> 32);
+        for (int i = threadIdx.x; i < nq * (int)(sizeof(PaprChainItem) / 8); i += XT_CHAIN_T)
+            reinterpret_cast<u64 *>(sh.item)[i] = ld_volatile(reinterpret_cast<const u64 *>(src->item) + i);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (stq == XT_NONFINITE) { if (s_st == XT_OK) s_st = XT_NONFINITE; }
+            else if (stq != XT_OK) { if (s_st != XT_FALLBACK) { s_st = XT_FALLBACK; s_why = (int)ld_volatile(reinterpret_cast<const u64 *>(src) + 1) & 0xffff; } }
+            else if (s_st == XT_OK) {
+                double s = s_state;
+                int why = XW_NONE;
+                s_st = xt_walk(sh.item, nq, &s, &why);
+                s_why = why;
+                s_state = s;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out->status = s_st; out->why = s_why; out->exact = s_state; }
+}
+
+void papr_launch_xt_chain_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
+                            const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
+                            const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
+                            unsigned long long seq, cudaStream_t s)
+{
+    XtCtx c;
+    c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
+    c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
+    c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
+    papr_xt_chain_x_kernel<<<1, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq);
 }

@@ -210,7 +210,8 @@ __device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, Papr
 // double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
 __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
                                  PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
-                                 size_t stride_bytes = sizeof(PaprDevStats))
+                                 size_t stride_bytes = sizeof(PaprDevStats), const PaprChainList *chain = nullptr,
+                                 int *chain_report = nullptr)
 {
     __shared__ int s_L;
     __shared__ double s_avg;
@@ -225,6 +226,12 @@ __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const Pa
             m.flags |= q.flags;
         }
         if (!isfinite(m.sum)) m.flags |= PAPR_FLAG_NONFINITE;
+        if (chain) { // the sequential sum chained over all shards on the device replaces the approximate one
+            const int st = chain->status;
+            if (st == XT_OK) m.sum = chain->exact;
+            chain_report[0] = st;
+            chain_report[1] = chain->why;
+        }
         *merged = m;
         double avg = __ddiv_rn(m.sum, (double)(long long)m.n);
         double ratio = __ddiv_rn((double)__int_as_float(m.val[TR_PEAK]), avg);
@@ -281,15 +288,16 @@ void papr_launch_finalize_levels(const PaprCtaPartial *wp, int nctas, u64 n, Pap
 
 __global__ void __launch_bounds__(FIN_T) papr_levels_kernel(const PaprDevStats *parts, int nparts, PaprTables tb,
                                                            int graph, PaprDevStats *merged, PaprDevLevels *lv,
-                                                           u64 *status_word)
+                                                           u64 *status_word, const PaprChainList *chain, int *chain_report)
 {
-    merge_and_levels(parts, nparts, tb, graph, merged, lv, status_word);
+    merge_and_levels(parts, nparts, tb, graph, merged, lv, status_word, sizeof(PaprDevStats), chain, chain_report);
 }
 
 void papr_launch_levels(const PaprDevStats *parts, int nparts, PaprTables t, int graph,
-                        PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word, cudaStream_t s)
+                        PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word, cudaStream_t s,
+                        const PaprChainList *chain, int *chain_report)
 {
-    papr_levels_kernel<<<1, FIN_T, 0, s>>>(parts, nparts, t, graph, merged, lv, status_word);
+    papr_levels_kernel<<<1, FIN_T, 0, s>>>(parts, nparts, t, graph, merged, lv, status_word, chain, chain_report);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -628,70 +636,7 @@ void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const 
 // values instead of three collective launches in between.  papr_device.cuh: PaprXchg.
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
-{
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ u64 ld_volatile(const u64 *p)
-{
-    u64 v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ u64 global_timer_ns()
-{
-    u64 t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// All threads of ONE CTA: copy `words` u64 from src into the field at `field_off` of slot[rank] in
-// every rank's window (NVLink stores for the peers, a local store for the own window), then raise
-// flag[kind][rank] = seq everywhere with a system-scope release.
-__device__ void xchg_publish(const PaprPeers &pp, int kind, size_t field_off, const u64 *src, int words, u64 seq)
-{
-    for (int r = 0; r < pp.world; ++r) {
-        u64 *dst = reinterpret_cast<u64 *>(reinterpret_cast<char *>(&pp.win[r]->slot[pp.rank]) + field_off);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->flag[kind][pp.rank], seq);
-}
-
-// All threads of ONE CTA: wait until every rank's publication `seq` of `kind` has landed in the own
-// window.  Returns false if a peer did not show up within pp.timeout_ns (tunable "xchg_timeout_s") or
-// some rank already gave up: the rank that times out raises its abort word in EVERY window before it
-// returns, so a peer that arrives late finds it and fails as well - all ranks agree on the outcome.
-__device__ bool xchg_wait(const PaprPeers &pp, int kind, u64 seq)
-{
-    __shared__ int s_late;
-    if (threadIdx.x == 0) s_late = 0;
-    __syncthreads();
-    if ((int)threadIdx.x < pp.world) {
-        const u64 *f = &pp.win[pp.rank]->flag[kind][threadIdx.x];
-        const u64 *ab = &pp.win[pp.rank]->abort[threadIdx.x];
-        const u64 t0 = global_timer_ns();
-        while (ld_acquire_sys(f) < seq) {
-            if (ld_volatile(ab) != 0 || global_timer_ns() - t0 > pp.timeout_ns) { atomicExch(&s_late, 1); break; }
-            __nanosleep(200);
-        }
-        if (ld_volatile(ab) != 0) atomicExch(&s_late, 1);
-    }
-    __syncthreads();
-    const bool late = s_late != 0;
-    if (late && (int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->abort[pp.rank], seq);
-    return !late;
-}
+#include "papr_xchg.cuh"
 
 // fused mode, sharded: fold this GPU's presample triples, publish them, wait for the other ranks',
 // add them up in rank order (identical on every rank) and plan from the global prediction
@@ -734,7 +679,7 @@ __global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const Pap
                                                                       PaprDevStats *local, PaprTables tb, int graph,
                                                                       PaprDevStats *merged, PaprDevLevels *lv,
                                                                       u64 *status_word, PaprPlan *plan, PaprPeers pp,
-                                                                      u64 seq)
+                                                                      u64 seq, PaprDevStats *parts_out)
 {
     reduce_partials(wp, nctas, n, local);
     __threadfence();
@@ -749,14 +694,20 @@ __global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const Pap
         reinterpret_cast<u64 *>(&s_parts[q])[w] = ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats) + w);
     }
     __syncthreads();
+    if (parts_out) { // the chain kernel comes first (it needs every shard's approximate sum); levels after it
+        for (int i = threadIdx.x; i < pp.world * (int)(sizeof(PaprDevStats) / 8); i += blockDim.x)
+            reinterpret_cast<u64 *>(parts_out)[i] = reinterpret_cast<const u64 *>(s_parts)[i];
+        return;
+    }
     merge_and_levels(s_parts, pp.world, tb, graph, merged, lv, status_word);
 }
 
 void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
-                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)
+                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s, PaprDevStats *parts_out)
 {
-    papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq);
+    papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq,
+                                                      parts_out);
 }
 
 // sharded: publish this shard's level counts (+ status word), collect every rank's, add them up.

@@ -425,9 +425,10 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
     one all-reduce (sum) of the integer level counts.  Returns the whole-capture result on every rank.
 
     exact_sum: emulate the reference's sequential double sum (papr.c:104) bit for bit across the
-    ranks (tile runs computed in parallel, chained rank after rank; adds world_size tiny broadcasts).
-    Default (None): on for host-resident shards, like the engine's own file/host path; off for
-    device-resident shards, whose merged fixed-order tree sums agree with it to ~1e-15 relative.
+    ranks.  Default (None) = on.  Device-resident shards in fused mode get it inside the single sweep
+    (papr_shard_analyze_p2p: per-tile runs from the TMA-fed scan, the chains of all ranks exchanged over
+    NVLink and walked on every GPU); otherwise tile runs are computed per rank and chained rank after
+    rank (world_size tiny broadcasts).  False: any fixed summation order (faster on the NCCL path).
     """
     import torch
     import torch.distributed as dist
@@ -436,9 +437,13 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
     backend = dist.get_backend(group) if dist.is_initialized() else "none"
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     if exact_sum is None:
-        exact_sum = host_image is not None
-    if backend == "nccl" and isinstance(engine, Engine) and host_image is None and not exact_sum:
-        return _analyze_sharded_stream_ordered(engine, d_iq, nsamples, first_index, bool(graph), mode, group)
+        exact_sum = True
+    partial = None
+    if backend == "nccl" and isinstance(engine, Engine) and host_image is None:
+        res, done = _analyze_sharded_stream_ordered(engine, d_iq, nsamples, first_index, bool(graph), mode, group, exact_sum)
+        if done:
+            return res
+        partial = res  # everything but the sequential sum (the device chain declined): patched in below
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     graph = bool(graph)
 
@@ -466,6 +471,20 @@ def analyze_sharded(engine, d_iq, nsamples: int, first_index: int, graph: bool, 
         v = t.tolist()
         return v[:-1], v[-1]
 
+    if partial is not None:
+        # statistics, and counts for the levels of the approximate sum, are in hand: chain the sequential sum rank
+        # after rank, re-derive the levels, and recount only if one of them moved
+        merged = PaprStats.from_buffer_copy(bytes(partial.stats))
+        if merged.sum == merged.sum and abs(merged.sum) != float("inf"):
+            merged.sum = _chain_sequential_sum(engine, d_iq, nsamples, rank, world, dev, group, merged.sum)
+        _avg, _papr, lv = levels(merged, graph)
+        if lv == partial.levels():
+            counts = partial.counts()
+        else:
+            counts, _ = allreduce_counts(engine.ccdf_shard(d_iq, nsamples, lv))
+        out = result_from_parts(merged, graph, counts)
+        out.mode_used, out.fused_miss, out.sum_path = partial.mode_used, partial.fused_miss, partial.sum_path
+        return out
     if host_image is not None:  # shard in (pinned) host memory: H2D + pass 1 overlapped, then resident
         mode = MODE_TWO_PASS
         local, d_iq, nsamples = engine.stats_shard_host(host_image, nsamples * 8, first_index)
@@ -583,11 +602,15 @@ def detach_peer_exchange(engine: "Engine", group=None) -> None:
         dist.barrier(group=group)
 
 
-def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group):
-    """Device-resident shards, one process per GPU.  Fused mode: ONE library call per rank, the three
-    exchanges happen inside the kernels over peer memory (papr_shard_analyze_p2p).  Otherwise (two-pass
-    mode, or peer mapping unavailable) the NCCL path: kernels and three tiny collectives enqueued back
-    to back on the engine's stream, in place on the engine's device buffers; one host synchronisation."""
+def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_index, graph, mode, group, exact_sum=True):
+    """Device-resident shards, one process per GPU.  Fused mode: ONE library call per rank, the
+    exchanges happen inside the kernels over peer memory (papr_shard_analyze_p2p), the sequential sum
+    included.  Otherwise (two-pass mode, or peer mapping unavailable) the NCCL path: kernels and three
+    tiny collectives enqueued back to back on the engine's stream, in place on the engine's device
+    buffers; one host synchronisation - its sum is a fixed-order tree sum, so it only serves callers
+    that said exact_sum=False.  Returns (result, done): done=False means the caller still has to supply
+    the sequential sum (result = everything else, or None: nothing computed yet); every rank reaches the
+    same verdict (the chain's status and a failed exchange are agreed on the device)."""
     import torch
     import torch.distributed as dist
 
@@ -598,7 +621,19 @@ def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_inde
         if p2p is None:
             p2p = engine._p2p = attach_peer_exchange(engine, group)
         if p2p:
-            return engine.shard_analyze_p2p(d_iq, nsamples, first_index, graph)
+            try:
+                res = engine.shard_analyze_p2p(d_iq, nsamples, first_index, graph)
+            except PaprError:
+                # a rank did not show up in time: every rank gets the same error (abort words in the windows),
+                # so all of them drop the windows together and continue over NCCL
+                engine._p2p = False
+                res = None
+            if res is not None:
+                declined = (res.sum_path & 0xff) == 2
+                small = (res.sum_path & 0xff) == 0 and res.stats.sum == res.stats.sum and abs(res.stats.sum) != float("inf")
+                return res, (not exact_sum or not (declined or small))
+    if exact_sum:
+        return None, False
     st = getattr(engine, "_xchg", None)
     if st is None:
         st = engine._xchg = {
@@ -624,7 +659,7 @@ def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_inde
             if miss2:
                 raise PaprError("exact CCDF pass reported a miss")
             res.fused_miss = 1
-    return res
+    return res, True
 
 
 # ---- the process boundary --------------------------------------------------------------------------

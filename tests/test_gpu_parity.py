@@ -250,7 +250,8 @@ def test_full_size_properties(built, eng, torch_cuda, log2n):
     h = n // 2
     parts = [eng.stats_shard(d, h, 0), eng.stats_shard(d[2 * h:], n - h, h)]
     m = built.merge_stats(parts)
-    assert m.as_tuple()[2:] == res.stats.as_tuple()[2:] and abs(m.sum - res.stats.sum) <= 1e-13 * m.sum
+    # (shard statistics carry fixed-order sums; the whole-capture result carries the reference's sequential sum)
+    assert m.as_tuple()[2:] == res.stats.as_tuple()[2:] and abs(m.sum - res.stats.sum) <= 1e-10 * m.sum
     lv = res.levels()
     c2 = np.array(eng.ccdf_shard(d, h, lv)) + np.array(eng.ccdf_shard(d[2 * h:], n - h, lv))
     assert c2.tolist() == res.counts()

@@ -80,9 +80,16 @@ for graph in (False, True):
     for mode in (1, 2):
         res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=mode)
         ok &= pb.format_result(res) == want
+        # the DEFAULT is the reference's sequential sum over the whole capture, bit for bit, on every rank
+        ok &= struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
     ok &= eng._p2p is True          # mode 2 ran with the exchanges inside the kernels over NVLink peer memory
-    eng._p2p = False                # the NCCL path: same text
-    ok &= pb.format_result(pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)) == want
+    # ... and its sum came from the chain built inside the sweep, exchanged over NVLink and walked on every GPU
+    res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)
+    ok &= (res.sum_path & 0xff) == 1
+    if not ok: print("rank", rank, "graph", graph, "sum_path", res.sum_path, flush=True)
+    eng._p2p = False                # the NCCL path: same text (fixed-order sum when the caller waives exactness)
+    ok &= pb.format_result(pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2, exact_sum=False)) == want
+    ok &= struct.pack("<d", pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2).stats.sum) == struct.pack("<d", seq_sum)
     eng._p2p = True
     eng.set("predict_bias", 1.05)   # forced miss: every rank must take the exact-pass branch together
     res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)
