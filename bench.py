@@ -197,6 +197,81 @@ def bind_to_gpu_numa_node(local):
 
 
 # ---- our arm ------------------------------------------------------------------------------------------
+def scan_traffic(graph, n, chained):
+    """DRAM bytes the dominant kernel moves per launch: bytes per sample from the committed `ncu --set full`
+    captures of this kernel (profiles/scan_traffic.json: one entry per mode), scaled to this shard."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json")))
+        e = t["modes"][("tma_" if chained else "ldg_") + ("graph" if graph else "1dB")]
+        return e["dram_bytes_per_sample"] * n, e["source"]
+    except Exception:
+        return None, None
+
+
+def roofline_of(mres, n, graph, peak, peak_src, world):
+    """`roofline` object for the dominant kernel of a measurement (one scan launch per 2^31 samples)."""
+    res = mres["res"]
+    scan_launch_ms = mres["scan_ms"] / mres["steps"]
+    achieved = BYTES_PER_SAMPLE * n / (scan_launch_ms * 1e-3) / 1e9
+    fused = res.mode_used == 2
+    chained = (res.sum_path & 0xff) == 1
+    traffic, tsrc = scan_traffic(graph, n * (1 if fused else 2), chained)
+    return {"bound": "hbm",
+            "kernel": ("papr_scan_tma_kernel (stats + CCDF + sequential sum, one sweep)" if chained else
+                       "papr_scan_kernel<stats,hist>" if fused else "papr_scan_kernel<stats> + papr_scan_kernel<hist>"),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": tsrc, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n * (1 if fused else 2), "launch_ms": scan_launch_ms,
+            "launches_per_step": max(1, -(-n >> 31)) * (1 if fused else 2)}
+
+
+def check_sharded_parity(pb, torch, dist, eng, d, n, first, graph, rank, world, stdout_p2p):
+    """N > 1: (1) at full size the in-kernel (NVLink peer memory) exchange and the NCCL exchange give the same
+    text on every rank; (2) a small capture sharded over the ranks gives the oracle's text for the concatenation
+    (rank 0 holds the checker; oracle use = checking only) and the same sequential-sum bits."""
+    import struct
+    out = {}
+    p2p = getattr(eng, "_p2p", None)
+    eng._p2p = False
+    res_nccl = pb.analyze_sharded(eng, d, n, first, graph, mode=pb.papr.MODE_FUSED)
+    eng._p2p = p2p
+    same = pb.format_result(res_nccl) == stdout_p2p
+    ns = 1 << 22
+    small = torch.empty(2 * ns, dtype=torch.float32, device="cuda")
+    eng.siggen(small, rank * ns, ns, 7)
+    ok_small = True
+    for g in (False, True):
+        r = pb.analyze_sharded(eng, small, ns, rank * ns, g, mode=pb.papr.MODE_FUSED)
+        if rank == 0:
+            import oracle_binding
+            whole = oracle_binding.siggen(0, world * ns, 7)
+            ok_small &= pb.format_result(r) == oracle_binding.run_image(whole.tobytes(), g)
+            ok_small &= struct.pack("<d", r.stats.sum) == struct.pack("<d", oracle_binding.analyze(whole, False)[0].sum)
+    t = torch.tensor([1 if same else 0, 1 if ok_small else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    out["p2p_equals_nccl_exchange_full_size"] = bool(t[0].item())
+    out["small_capture_equals_oracle"] = bool(t[1].item())
+    out["small_capture"] = "%d x 2^22 samples, seed 7, 1 dB and -g, text + sequential-sum bits" % world
+    return out
+
+
+def h2d_ceiling(torch, pinned, d, barrier, reps=2):
+    """What plain pinned->device copies of the same buffer reach with every rank copying at once (the ceiling of
+    the e2e leg at this N): GB/s of this rank."""
+    nb = pinned.numel() * 4
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(reps + 1):
+        barrier()
+        ev0.record()
+        d[:pinned.numel()].copy_(pinned, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        best = ms if best is None else min(best, ms)
+    return nb / best / 1e6
+
+
 def run_ours(args):
     import torch
     import dtv_utils_b200 as pb
@@ -218,12 +293,13 @@ def run_ours(args):
     graph = bool(args.graph)
     eng = pb.Engine(local)
     mode = {"auto": 0, "two_pass": 1, "fused": 2}[args.mode]
-    eng.set("mode", mode)
+    n_big = max(n, 1 << 32) if not args.no_configs else n   # one allocation serves the main workload and c3 / c4
+    big = torch.empty(2 * n_big, dtype=torch.float32, device="cuda")
+    d = big[:2 * n]
     if args.signal == "ofdm32k":  # DVB-T2-like 32K OFDM (BASELINE configs[4]); same base block on every rank
         from dtv_utils_b200.producers import ofdm_capture
-        d = ofdm_capture(n, seed=1 + rank, device="cuda")
+        d.copy_(ofdm_capture(n, seed=1 + rank, device="cuda"))
     else:
-        d = torch.empty(2 * n, dtype=torch.float32, device="cuda")
         eng.siggen(d, first, n, 1)
     torch.cuda.synchronize()
 
@@ -232,38 +308,63 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        if world == 1:
-            return eng.analyze_device(d, n, graph)
-        return pb.analyze_sharded(eng, d, n, first, graph, mode=pb.papr.MODE_FUSED if mode != 1 else 1)
-
     ext = torch.cuda.ExternalStream(eng.stream)
+
+    def run_resident(buf, ns, first_idx, g, steps, warmup):
+        """W untimed + K timed analyses of the resident shard `buf` (times local to this rank)."""
+        def one():
+            if world == 1:
+                return eng.analyze_device(buf, ns, g)
+            return pb.analyze_sharded(eng, buf, ns, first_idx, g, mode=pb.papr.MODE_FUSED if mode != 1 else 1)
+        for _ in range(warmup):
+            r = one()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        la = d2 = 0
+        sc = dv = 0.0
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(steps):
+            r = one()
+            la += r.kernel_launches
+            sc += r.scan_ms
+            dv += r.device_ms
+            d2 += r.d2h_bytes
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        ev = e0.elapsed_time(e1)
+        # a step ends with a host synchronisation, so wall >= the device span; take the larger (honest) one
+        return {"t": max(wall, ev * 1e-3), "ev_ms": ev, "launches": la, "scan_ms": sc, "dev_ms": dv, "d2h": d2,
+                "res": r, "steps": steps}
+
+    def reduce_max(m):
+        if dist is None:
+            return m
+        t = torch.tensor([m["t"], m["scan_ms"], m["dev_ms"], m["ev_ms"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        m["t"], m["scan_ms"], m["dev_ms"], m["ev_ms"] = t.tolist()
+        lt = torch.tensor([m["launches"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        m["launches"] = int(lt.item())
+        return m
+
+    eng.set("mode", mode)
     sampler = ClockSampler(local)
     sampler.start()
 
     # ---- value: shard resident in HBM ---------------------------------------------------------------
-    for _ in range(args.warmup):
-        res = step_resident()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches, scan_ms, dev_ms = 0, 0.0, 0.0
-    t0 = time.perf_counter()
-    ev0.record(ext)
-    for _ in range(args.steps):
-        res = step_resident()
-        launches += res.kernel_launches
-        scan_ms += res.scan_ms
-        dev_ms += res.device_ms
-    ev1.record(ext)
-    barrier()
-    wall = time.perf_counter() - t0
-    ev_ms = ev0.elapsed_time(ev1)
-    # a step ends with a host synchronisation, so wall >= the device span; take the larger (honest) one
-    t_rank = max(wall, ev_ms * 1e-3)
+    m = reduce_max(run_resident(d, n, first, graph, args.steps, args.warmup))
+    res = m["res"]
     stdout_resident = pb.format_result(res)
 
+    # ---- N > 1: is the merged answer right? ------------------------------------------------------------
+    sharded_parity = None
+    if world > 1:
+        sharded_parity = check_sharded_parity(pb, torch, dist, eng, d, n, first, graph, rank, world, stdout_resident)
+
     # ---- e2e: capture in pinned host memory, H2D inside the timed region ------------------------------
-    n_host, e2e_steps, t_e2e, h2d, d2h, pinned = n, 0, 1.0, 0, 0, None
+    n_host, e2e_steps, t_e2e, h2d, d2h, pinned, ceil_gbs = n, 0, 1.0, 0, 0, None, None
     if args.e2e_steps > 0:  # (0 only for profiling runs under ncu)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         import psutil
@@ -275,78 +376,108 @@ def run_ours(args):
         pinned = torch.empty(2 * n_host, dtype=torch.float32, pin_memory=True)
         pinned.copy_(d[:2 * n_host])
         torch.cuda.synchronize()
+        scratch = big[2 * n:2 * n + 2 * n_host] if n_big >= n + n_host else torch.empty(2 * n_host, dtype=torch.float32, device="cuda")
+        ceil_gbs = h2d_ceiling(torch, pinned, scratch, barrier)
         if world == 1:
             def step_host():
-                return eng.analyze_host(pinned, graph=graph)
+                r = eng.analyze_host(pinned, graph=graph)
+                return r, r.h2d_bytes, r.d2h_bytes
         else:
-            class _Acc:
-                h2d_bytes = 0
-                d2h_bytes = 0
-
-            def step_host():  # every rank streams its own shard in; same two exchanges as the resident path
-                pb.analyze_sharded(eng, None, n_host, rank * n_host, graph, host_image=pinned)
-                _Acc.h2d_bytes, _Acc.d2h_bytes = n_host * 8, 4096
-                return _Acc
+            def step_host():  # every rank streams its own shard in; same exchanges as the resident path
+                r = pb.analyze_sharded(eng, None, n_host, rank * n_host, graph, host_image=pinned)
+                # bytes this rank moved: the shard itself, its statistics / tile sums and runs / level counts
+                nt = -(-n_host // 32768)
+                return r, n_host * 8, 104 + nt * 24 + 8 * (r.nlevels + 1)
         for _ in range(min(2, args.warmup)):
-            hres = step_host()
+            hres, _, _ = step_host()
         barrier()
-        h2d = d2h = 0
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            hres = step_host()
-            h2d += hres.h2d_bytes
-            d2h += hres.d2h_bytes
+            hres, bi, bo = step_host()
+            h2d += bi
+            d2h += bo
         barrier()
         t_e2e = time.perf_counter() - t0
+
+    # ---- the other BASELINE configurations, briefly (same GPUs, resident) --------------------------------
+    subs = {}
+    if not args.no_configs and args.signal == "appendixA":
+        ks, kw = max(3, min(5, args.steps)), 3
+
+        def sub(name, what, buf, ns, first_idx, g):
+            mm = reduce_max(run_resident(buf, ns, first_idx, g, ks, kw))
+            r = mm["res"]
+            subs[name] = {"workload": what, "graph": g, "samples_per_gpu": ns, "value": world * ns * ks / mm["t"] / 1e9,
+                          "unit": UNIT, "ms_per_step": mm["t"] / ks * 1e3, "hbm_pct_of_8tbs": ns * ks / mm["t"] / 1e9 * 8 / 80 / 1,
+                          "scan_ms_per_step": mm["scan_ms"] / ks, "fused_miss": int(r.fused_miss), "levels": int(r.nlevels),
+                          "exact_sum": (r.sum_path & 0xff) == 1, "sum_path": int(r.sum_path & 0xff),
+                          "roofline_frac_of_measured": BYTES_PER_SAMPLE * ns / (mm["scan_ms"] / ks * 1e-3) / 1e9 / measured_peak()[0]}
+            return r
+        nb = 1 << 32
+        if n_big >= nb:
+            eng.siggen(big, rank * nb, nb, 2)
+            torch.cuda.synchronize()
+            sub("c3_graph_32gib", "papr -g on 32 GiB per GPU (BASELINE configs[2]); seed 2", big, nb, rank * nb, True)
+            sub("c4_1dB_32gib_per_gpu", "papr 1 dB on 32 GiB per GPU = %d GiB byte-range-sharded over %d GPU(s) (BASELINE configs[3])"
+                % (32 * world, world), big, nb, rank * nb, False)
+        from dtv_utils_b200.producers import ofdm_capture
+        d.copy_(ofdm_capture(n, seed=1 + rank, device="cuda"))
+        torch.cuda.synchronize()
+        sub("c5_ofdm32k_graph", "papr -g on a DVB-T2-like 32K OFDM capture, %d GiB per GPU (BASELINE configs[4])" % (n * 8 >> 30),
+            d, n, first, True)
 
     sampler.stop_flag = True
     sampler.join(1.0)
 
     # ---- max over ranks ------------------------------------------------------------------------------------
     if dist is not None:
-        t = torch.tensor([t_rank, t_e2e, scan_ms, dev_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([t_e2e, -(ceil_gbs or 0.0)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_rank, t_e2e, scan_ms, dev_ms = t.tolist()
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt)
-        launches = int(lt.item())
+        t_e2e, ceil_min = t[0].item(), -t[1].item()
+        ts = torch.tensor([ceil_gbs or 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts)
+        ceil_sum = ts.item()
+    else:
+        ceil_min = ceil_sum = ceil_gbs or 0.0
 
     if rank == 0:
-        value = world * n * args.steps / t_rank / 1e9
+        value = world * n * args.steps / m["t"] / 1e9
         e2e_value = world * n_host * e2e_steps / t_e2e / 1e9 if e2e_steps else None
         peak, peak_src = measured_peak()
-        scan_launch_ms = scan_ms / args.steps          # dominant kernel: papr_scan_kernel (one launch per step)
-        achieved = BYTES_PER_SAMPLE * n / (scan_launch_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                pass
+        roof = roofline_of(m, n, graph, peak, peak_src, world)
+        roof["headline_frac_all_kernels"] = value / world * BYTES_PER_SAMPLE / peak
+        chained = (res.sum_path & 0xff) == 1
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": t_rank / args.steps * 1e3, "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": m["t"] / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(workload_config(args, n), mode=("fused" if res.mode_used == 2 else "two_pass"),
                                parallelism="byte-range x%d" % world,
                                exchange=("none (single shard)" if world == 1 else
                                          "in-kernel over NVLink peer memory" if getattr(eng, "_p2p", False) else "nccl")),
+                # papr.c:104: is stats.sum the reference's sequential double sum, bit for bit, on the timed path?
+                "exact_sum": bool(chained or (res.sum_path & 0xff) in (2, 3)),
+                "sum_path": {0: "fixed-order (not emulated)", 1: "emulated inside the sweep, chained on the device",
+                             2: "two-sweep emulation", 3: "emulated while streaming in"}.get(res.sum_path & 0xff),
                 "hbm_gbs": value * BYTES_PER_SAMPLE, "hbm_pct_of_8tbs": value * BYTES_PER_SAMPLE / 8000 * 100,
-                "device_ms_per_step": dev_ms / args.steps, "event_ms_per_step": ev_ms / args.steps,
-                "roofline": {"bound": "hbm", "kernel": "papr_scan_kernel<stats,hist>" if res.mode_used == 2
-                             else "papr_scan_kernel<stats> + papr_scan_kernel<hist>",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n * (1 if res.mode_used == 2 else 2),
-                             "launch_ms": scan_launch_ms,
-                             "headline_frac_all_kernels": value / world * BYTES_PER_SAMPLE / peak},
+                "device_ms_per_step": m["dev_ms"] / args.steps, "event_ms_per_step": m["ev_ms"] / args.steps,
+                "roofline": roof,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(e2e_steps, 1),
                         "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
-                        "samples_per_gpu": n_host, "host_memory": "pinned"},
-                "gpu_launches": launches, "clocks": sampler.result(), "fused_miss": int(res.fused_miss)}
+                        "samples_per_gpu": n_host, "host_memory": "pinned",
+                        # plain cudaMemcpyAsync of the same pinned buffers, all ranks at once: what the box allows
+                        "h2d_ceiling_gbs_all_ranks": ceil_sum, "h2d_ceiling_gbs_slowest_rank": ceil_min,
+                        "frac_of_h2d_ceiling": (e2e_value * BYTES_PER_SAMPLE / ceil_sum) if (e2e_value and ceil_sum) else None},
+                "gpu_launches": m["launches"], "clocks": sampler.result(), "fused_miss": int(res.fused_miss)}
+        if subs:
+            line["configs"] = subs
+        if sharded_parity is not None:
+            line["sharded_parity"] = all(v for v in sharded_parity.values() if isinstance(v, bool))
+            line["sharded_parity_detail"] = sharded_parity
         if world == 1 and pinned is not None and n_host == n:
-            # the drop-in path (exact sequential sum) and the timed resident path print the same text
+            # the drop-in path and the timed resident path print the same text and hold the same sum bits
+            import struct
             line["resident_stdout_equals_host_path_stdout"] = bool(pb.format_result(hres) == stdout_resident)
+            line["resident_sum_bits_equal_host_path_sum_bits"] = bool(struct.pack("<d", hres.stats.sum) == struct.pack("<d", res.stats.sum))
         if world == 1 and not args.no_cpu and pinned is not None:
             line["cpu_baseline"] = cpu_baseline(args, pinned, n_host, graph, eng, pb)
         print(json.dumps(line), flush=True)
@@ -379,8 +510,11 @@ def main():
     # stdout carries exactly one JSON line: keep NCCL's banner / debug output (NCCL_DEBUG=VERSION is set
     # on some boxes) on stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":  # this level ignores NCCL_DEBUG_FILE
-        os.environ["NCCL_DEBUG"] = "WARN"
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        # this level prints its banner on stdout whatever NCCL_DEBUG_FILE says; INFO/INIT honours the file, so the
+        # rank / topology lines a reader of the log looks for still appear - on stderr
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -392,6 +526,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2-samples", type=int, default=28)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c4 / c5 sub-records")
     ap.add_argument("--signal", default="appendixA", choices=["appendixA", "ofdm32k"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
