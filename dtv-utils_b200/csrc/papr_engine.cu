@@ -1587,14 +1587,17 @@ static TileFetch tile_fetcher(papr_engine *e, const HostSource &src, const Strea
 // unless inline_exact.
 enum SeqInline { SEQ_NONE = 0, SEQ_SUMS_ONLY = 1, SEQ_FULL = 2 };
 
-static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, SeqInline seq,
-                      bool *exact_done)
+// who delivers the chunks: a seekable source streamed by stream_chunks, or a pipe read once (stream_fd_chunks,
+// which also fills in the geometry - the length of a pipe is known only at its end)
+typedef std::function<int(const ChunkWork &work)> ChunkDriver;
+
+static int host_pass1_driver(papr_engine *e, StreamGeom &g, u64 max_tiles, bool resident, SeqInline seq, bool *exact_done,
+                             const ChunkDriver &drive, const TileFetch &fetch)
 {
     int rc;
     *exact_done = false;
     const bool inline_exact = seq == SEQ_FULL;
-    const u64 ntiles = (g.n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
-    if (seq != SEQ_NONE && (rc = ensure_seq_buffers(e, std::max<u64>(ntiles, 1)))) return rc;
+    if (seq != SEQ_NONE && (rc = ensure_seq_buffers(e, std::max<u64>(max_tiles, 1)))) return rc;
     if ((rc = enqueue_reset(e))) return rc;
 
     struct Pending { const float *d; u64 off, m, c; };
@@ -1618,7 +1621,7 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
         release(ch.c);
         return PAPR_OK;
     };
-    rc = stream_chunks(e, src, g, resident, [&](const float *d, u64 off, u64 m, u64 c, bool last, const ChunkRelease &release) -> int {
+    rc = drive([&](const float *d, u64 off, u64 m, u64 c, bool last, const ChunkRelease &release) -> int {
         int r = enqueue_scan(e, true, false, d, m, g.first + off, false);
         if (r) return r;
         if (seq == SEQ_NONE) { release(c); return PAPR_OK; }
@@ -1635,6 +1638,7 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
         return PAPR_OK;
     });
     if (rc) return rc;
+    const u64 ntiles = (g.n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE;
     papr_launch_stats_finalize(e->d_work->wp, e->grid, g.n, &e->d_out->local, e->stream);
     e->launches += 1;
     CU(cudaGetLastError());
@@ -1644,12 +1648,21 @@ static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g
     CU(cudaStreamSynchronize(e->stream));
     e->d2h += ntiles * 16;
     double s = 0.0;
-    rc = seq_chain(e, g.n, &s, tile_fetcher(e, src, g, resident));
+    rc = seq_chain(e, g.n, &s, fetch);
     if (rc) return rc;
     e->h_out->pre4[0] = s;
     CU(cudaMemcpyAsync(&e->d_out->local.sum, &e->h_out->pre4[0], sizeof(double), cudaMemcpyHostToDevice, e->stream));
     *exact_done = true;
     return PAPR_OK;
+}
+
+static int host_pass1(papr_engine *e, const HostSource &src, const StreamGeom &g, bool resident, SeqInline seq,
+                      bool *exact_done)
+{
+    StreamGeom gg = g;
+    return host_pass1_driver(e, gg, (g.n + PAPR_SEQ_TILE - 1) / PAPR_SEQ_TILE, resident, seq, exact_done,
+                             [&](const ChunkWork &work) { return stream_chunks(e, src, g, resident, work); },
+                             tile_fetcher(e, src, g, resident));
 }
 
 // CCDF pass of the re-streaming mode: the capture crosses PCIe a second time, chunk by chunk
@@ -1820,56 +1833,207 @@ extern "C" int papr_stats_host(papr_engine *e, const void *image, uint64_t bytes
     return fix_nan_sign(e, e->d_buf, n, first, out);
 }
 
-// The capture behind a path: a regular file is read with pread() chunk by chunk (page cache ->
-// pinned staging, no mapping); anything else (FIFO, character device - the reference needs a seekable
-// file, papr.c:142, we do not) is read to the end into memory first.
-struct FileSource {
-    HostSource src;
-    void *owned = nullptr;
-    int open(const char *path, std::string &err)
-    {
-        int fd = ::open(path, O_RDONLY);
-        if (fd < 0) { err = std::string("cannot open ") + path; return PAPR_ERR_IO; }
-        struct stat sb;
-        if (fstat(fd, &sb) != 0) { ::close(fd); err = "fstat failed"; return PAPR_ERR_IO; }
-        if (S_ISREG(sb.st_mode)) {
-            src.fd = fd;
-            src.bytes = (u64)sb.st_size;
-            posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-            return PAPR_OK;
-        }
-        size_t cap = 1u << 24, bytes = 0;
-        char *buf = (char *)malloc(cap);
-        for (;;) {
-            if (!buf) { ::close(fd); err = "out of memory reading the stream"; return PAPR_ERR_IO; }
-            ssize_t got = ::read(fd, buf + bytes, cap - bytes);
-            if (got < 0 && errno == EINTR) continue;
-            if (got < 0) { free(buf); ::close(fd); err = "read failed"; return PAPR_ERR_IO; }
-            if (got == 0) break;
-            bytes += (size_t)got;
-            if (bytes == cap) buf = (char *)realloc(buf, cap *= 2);
-        }
-        ::close(fd);
-        owned = buf;
-        src.img = (const unsigned char *)buf;
-        src.bytes = bytes;
-        return PAPR_OK;
-    }
-    ~FileSource()
-    {
-        if (src.fd >= 0) ::close(src.fd);
-        free(owned);
-    }
+// ------------------------------------------------------------------------------------------------
+// non-seekable inputs (FIFOs, pipes, character devices): the reference cannot read them at all - it rewinds
+// its file (papr.c:142).  Here the stream is read ONCE: every 4 MiB piece goes from read(2) into a pinned slot
+// and straight on to the GPU, pass 1 and the sequential-sum stages run on each 64 MiB chunk while the next is
+// still arriving, and the chunks stay resident in HBM for the CCDF pass.  Limit: the stream must fit the
+// GPU's free memory (less 1 GiB).
+// ------------------------------------------------------------------------------------------------
+struct StreamChunks {
+    std::vector<float *> dev; // one device buffer per chunk of chunk_samples (the last may hold fewer)
+    u64 chunk_samples = 0;
+    ~StreamChunks() { for (auto p : dev) cudaFree(p); }
 };
+
+static int stream_fd_chunks(papr_engine *e, int fd, StreamGeom *g, StreamChunks *sc, u64 max_bytes, const ChunkWork &work)
+{
+    int rc;
+    const size_t piece = piece_bytes_of(e);
+    const u64 chunk_bytes = e->chunk_bytes;
+    const ChunkRelease release = [](u64) {};
+    sc->chunk_samples = chunk_bytes / 8;
+    g->chunk_samples = sc->chunk_samples;
+    u64 total = 0;      // bytes read so far
+    u64 fill = 0;       // bytes in the current (last) chunk
+    u64 pending_c = 0;  // chunks handed to `work` so far
+    bool have_full = false; // the last chunk is full and not yet handed on (is it the final one? only the next read tells)
+    std::vector<unsigned char> recent; // the last <= 256 KiB of the stream (the stale Q of a lone trailing I lives there)
+    u64 recent_base = 0;
+    int slot = 0;
+    auto dispatch = [&](bool last) -> int {
+        const u64 c = pending_c++;
+        const u64 off = c * sc->chunk_samples;
+        const u64 m = last ? g->n - off : sc->chunk_samples;
+        CU(cudaEventRecord(e->chunk_ready, e->copy_stream));
+        CU(cudaStreamWaitEvent(e->stream, e->chunk_ready, 0));
+        return work(sc->dev[c], off, m, c, last, release);
+    };
+    for (;;) {
+        CU(cudaEventSynchronize(e->stage_done[slot])); // the slot's previous tenant has crossed PCIe
+        unsigned char *buf = (unsigned char *)e->h_stage[slot];
+        size_t got = 0;
+        while (got < piece) {
+            ssize_t k = ::read(fd, buf + got, piece - got);
+            if (k < 0 && errno == EINTR) continue;
+            if (k < 0) return fail(e, PAPR_ERR_IO, "read failed on the input stream");
+            if (k == 0) break;
+            got += (size_t)k;
+        }
+        if (got == 0) break;
+        if (total + got > max_bytes)
+            return fail(e, PAPR_ERR_ARG, "the input stream does not fit this GPU's memory; write it to a file first");
+        for (size_t done = 0; done < got;) { // a piece may straddle two chunks
+            if (have_full) { have_full = false; if ((rc = dispatch(false))) return rc; fill = 0; }
+            if (fill == 0) {
+                float *p = nullptr;
+                CU(cudaMalloc(&p, chunk_bytes + 16));
+                sc->dev.push_back(p);
+            }
+            const size_t take = (size_t)std::min<u64>(got - done, chunk_bytes - fill);
+            CU(cudaMemcpyAsync((char *)sc->dev.back() + fill, buf + done, take, cudaMemcpyHostToDevice, e->copy_stream));
+            fill += take; done += take;
+            if (fill == chunk_bytes) have_full = true;
+        }
+        CU(cudaEventRecord(e->stage_done[slot], e->copy_stream));
+        e->h2d += got;
+        // remember the tail of the stream
+        if (got >= (256u << 10)) { recent.assign(buf + got - (256u << 10), buf + got); recent_base = total + got - (256u << 10); }
+        else {
+            recent.insert(recent.end(), buf, buf + got);
+            if (recent.size() > (512u << 10)) { const size_t cut = recent.size() - (256u << 10); recent.erase(recent.begin(), recent.begin() + cut); recent_base += cut; }
+        }
+        total += got;
+        slot = (slot + 1) % e->h_stage_slots;
+        if (got < piece) break; // end of stream
+    }
+    // geometry, now that the length is known (papr.c:101-103: a lone trailing I still counts as a sample)
+    const u64 nfloats = total / 4;
+    g->npairs = nfloats / 2;
+    g->tail = (nfloats & 1) != 0;
+    g->n = g->npairs + (g->tail ? 1 : 0);
+    if (g->tail) {
+        auto byte_at = [&](u64 off) -> unsigned char { return off >= recent_base && off - recent_base < recent.size() ? recent[off - recent_base] : 0; };
+        const u64 chunk = 16384, last = nfloats - 1, slot_f = last % chunk + 1, chunk_start = last - last % chunk; // papr_host_stale_q
+        unsigned char q[4] = {0, 0, 0, 0}, ib[4];
+        for (int k = 0; k < 4; ++k) ib[k] = byte_at(4 * last + k);
+        if (chunk_start >= chunk) for (int k = 0; k < 4; ++k) q[k] = byte_at(4 * (chunk_start - chunk + slot_f) + k);
+        for (u64 k = 0; k < total % 4; ++k) q[k] = byte_at(4 * nfloats + k);
+        memcpy(&g->tail_pair[0], ib, 4);
+        memcpy(&g->tail_pair[1], q, 4);
+        // the tail sample sits right after the last complete pair: possibly the first sample of a fresh chunk
+        const u64 cidx = g->npairs / sc->chunk_samples;
+        if (cidx == sc->dev.size()) {
+            if (have_full) { have_full = false; if ((rc = dispatch(false))) return rc; }
+            float *p = nullptr;
+            CU(cudaMalloc(&p, 64));
+            sc->dev.push_back(p);
+        }
+        CU(cudaMemcpyAsync(sc->dev[cidx] + 2 * (g->npairs - cidx * sc->chunk_samples), g->tail_pair, 8, cudaMemcpyHostToDevice, e->copy_stream));
+        e->h2d += 8;
+    }
+    if (g->n > pending_c * sc->chunk_samples) return dispatch(true);
+    return PAPR_OK;
+}
+
+static int analyze_stream(papr_engine *e, int fd, int graph, papr_result *out)
+{
+    graph = graph ? 1 : 0;
+    begin_analysis(e);
+    reset_result(out);
+    out->mode_used = PAPR_MODE_TWO_PASS;
+    int rc;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const u64 budget = e->max_resident_bytes ? e->max_resident_bytes : (free_b > (1ull << 30) ? free_b - (1ull << 30) : 0);
+    if ((rc = ensure_staging(e))) return rc;
+    StreamGeom g;
+    StreamChunks sc;
+    const bool exact = e->exact_sum != 0;
+    CU(cudaEventRecord(e->ev_begin, e->stream));
+    bool exact_done = false;
+    const TileFetch fetch = [&](u64 first, u64 cnt, float *dst) -> int { // a tile never straddles chunks (chunks are whole tiles)
+        const u64 c = first / sc.chunk_samples;
+        CU(cudaMemcpyAsync(dst, sc.dev[c] + 2 * (first - c * sc.chunk_samples), cnt * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        e->d2h += cnt * 8;
+        return PAPR_OK;
+    };
+    rc = host_pass1_driver(e, g, budget / 8 / PAPR_SEQ_TILE + 2, true, exact ? SEQ_FULL : SEQ_NONE, &exact_done,
+                           [&](const ChunkWork &work) { return stream_fd_chunks(e, fd, &g, &sc, budget, work); }, fetch);
+    if (rc) return rc;
+    out->sum_path = exact_done ? 3u : 0u;
+    papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
+                       &e->d_out->counts[PAPR_MAX_LEVELS], e->stream);
+    e->launches += 1;
+    auto ccdf_pass = [&]() -> int { // the resident chunks, one launch each
+        int r;
+        if ((r = hist_begin(e))) return r;
+        for (size_t c = 0; c < sc.dev.size(); ++c) {
+            const u64 off = c * sc.chunk_samples, m = std::min<u64>(sc.chunk_samples, g.n - off);
+            if (m && (r = hist_chunk(e, sc.dev[c], m, false))) return r;
+        }
+        return hist_end(e);
+    };
+    if ((rc = ccdf_pass())) return rc;
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaEventRecord(e->ev_end, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    stats_to_host(e->h_out->o.merged, &out->stats);
+    if (std::isnan(out->stats.sum) && g.n) { // sign of the reference's printed "nan": the first NaN that entered the sum
+        CU(cudaMemsetAsync(e->d_nan_idx, 0xff, sizeof(u64), e->stream));
+        for (size_t c = 0; c < sc.dev.size(); ++c) {
+            const u64 off = c * sc.chunk_samples, m = std::min<u64>(sc.chunk_samples, g.n - off);
+            if (m) papr_launch_find_nan(sc.dev[c], m, off, e->d_nan_idx, e->num_sms * 8, e->stream);
+        }
+        CU(cudaMemcpyAsync(&e->h_out->nan_idx, e->d_nan_idx, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        const u64 k = e->h_out->nan_idx;
+        if (k != ~0ull) {
+            float pair[2];
+            if ((rc = fetch(k, 1, pair))) return rc;
+            const bool neg = std::isnan(pair[1]) ? std::signbit(pair[1]) : std::signbit(pair[0]);
+            out->stats.sum = std::copysign(std::fabs(out->stats.sum), neg ? -1.0 : 1.0);
+        }
+    }
+    if (collect(e, graph, out, true)) { // device level table != host libm's: redo with the host's
+        if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
+        if ((rc = enqueue_reset(e))) return rc;
+        if ((rc = ccdf_pass())) return rc;
+        if ((rc = enqueue_fetch(e))) return rc;
+        CU(cudaEventRecord(e->ev_end, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->h_out->o.counts[PAPR_MAX_LEVELS] != 0) return fail(e, PAPR_ERR_INTERNAL, "exact CCDF pass reported a miss");
+        for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)e->h_out->o.counts[j];
+    }
+    finish_timing(e, out);
+    return PAPR_OK;
+}
+
+// The capture behind a file descriptor: a regular file is read with pread() chunk by chunk (page cache ->
+// pinned staging, no mapping); anything else is streamed once (analyze_stream).
+extern "C" int papr_analyze_fd(papr_engine *e, int fd, int graph, papr_result *out)
+{
+    if (!e || fd < 0 || !out) return PAPR_ERR_ARG;
+    cudaSetDevice(e->device);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) return fail(e, PAPR_ERR_IO, "fstat failed");
+    if (!S_ISREG(sb.st_mode)) return analyze_stream(e, fd, graph, out);
+    HostSource src;
+    src.fd = fd;
+    src.bytes = (u64)sb.st_size;
+    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    return analyze_source(e, src, graph, out);
+}
 
 extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)
 {
     if (!e || !path || !out) return PAPR_ERR_ARG;
-    cudaSetDevice(e->device);
-    FileSource f;
-    int rc = f.open(path, e->err);
-    if (rc) return rc;
-    return analyze_source(e, f.src, graph, out);
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return fail(e, PAPR_ERR_IO, std::string("cannot open ") + path);
+    const int rc = papr_analyze_fd(e, fd, graph, out);
+    ::close(fd);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2180,11 +2344,31 @@ extern "C" int papr_multi_analyze_host(papr_multi *m, const void *image, uint64_
     return multi_analyze_source(m, memory_source(image, bytes), graph, out);
 }
 
+// a regular file is sharded by byte range over the GPUs; a pipe is read once by the first engine (the pipe,
+// not the GPU, is the limit there)
+extern "C" int papr_multi_analyze_fd(papr_multi *m, int fd, int graph, papr_result *out)
+{
+    if (!m || fd < 0 || !out) return PAPR_ERR_ARG;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { m->err = "fstat failed"; return PAPR_ERR_IO; }
+    if (!S_ISREG(sb.st_mode)) {
+        const int rc = papr_analyze_fd(m->eng[0], fd, graph, out);
+        if (rc) m->err = m->eng[0]->err;
+        return rc;
+    }
+    HostSource src;
+    src.fd = fd;
+    src.bytes = (u64)sb.st_size;
+    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+    return multi_analyze_source(m, src, graph, out);
+}
+
 extern "C" int papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out)
 {
     if (!m || !path || !out) return PAPR_ERR_ARG;
-    FileSource f;
-    int rc = f.open(path, m->err);
-    if (rc) return rc;
-    return multi_analyze_source(m, f.src, graph, out);
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) { m->err = std::string("cannot open ") + path; return PAPR_ERR_IO; }
+    const int rc = papr_multi_analyze_fd(m, fd, graph, out);
+    ::close(fd);
+    return rc;
 }

@@ -9,6 +9,8 @@
 #include <string.h>
 #include <strings.h>
 #include <time.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/papr_b200.h"
 
@@ -61,12 +63,13 @@ int papr_main(int argc, char **argv)
         }
         path = argv[2];
     }
-    FILE *fp = fopen(path, "r"); /* papr.c:62-66 / 93-97: same check, same message */
-    if (fp == NULL) {
+    /* papr.c:62-66 / 93-97: same check, same message.  Opened ONCE and handed down as a descriptor: a named
+     * FIFO must not be opened and closed just to probe it (its writer would see the reader disappear) */
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) {
         fprintf(stderr, "Cannot open bitstream file <%s>\n", path);
         return 255;
     }
-    fclose(fp);
 
     const char *v;
     papr_result *r = (papr_result *)calloc(1, sizeof(*r));
@@ -84,16 +87,18 @@ int papr_main(int argc, char **argv)
         if (papr_multi_create(ndev, devs, &m) != PAPR_OK) {
             fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_multi_last_error(NULL));
             free(r);
+            close(fd);
             return 1;
         }
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_multi_set(m, "chunk_bytes", atof(v) * 1048576.0);
         if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_multi_set(m, "staging_threads", atof(v));
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_multi_set(m, "exact_sum", atof(v));
-        int rc = papr_multi_analyze_file(m, path, graph, r);
+        int rc = papr_multi_analyze_fd(m, fd, graph, r);
         if (rc != PAPR_OK) {
             fprintf(stderr, "papr: %s\n", papr_multi_last_error(m));
             papr_multi_destroy(m);
             free(r);
+            close(fd);
             return 1;
         }
         if (getenv("PAPR_B200_STATS"))
@@ -108,6 +113,7 @@ int papr_main(int argc, char **argv)
         if (papr_engine_create(dev ? atoi(dev) : -1, &e) != PAPR_OK) {
             fprintf(stderr, "papr: GPU engine unavailable: %s\n", papr_last_error(NULL));
             free(r);
+            close(fd);
             return 1;
         }
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
@@ -115,12 +121,13 @@ int papr_main(int argc, char **argv)
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
         if ((v = getenv("PAPR_B200_MAX_RESIDENT_MB"))) papr_engine_set(e, "max_resident_bytes", atof(v) * 1048576.0);
         const double t1 = now_ms();
-        int rc = papr_analyze_file(e, path, graph, r);
+        int rc = papr_analyze_fd(e, fd, graph, r);
         const double t2 = now_ms();
         if (rc != PAPR_OK) {
             fprintf(stderr, "papr: %s\n", papr_last_error(e));
             papr_engine_destroy(e);
             free(r);
+            close(fd);
             return 1;
         }
         print_result(r);
@@ -132,5 +139,6 @@ int papr_main(int argc, char **argv)
                     (unsigned long long)r->h2d_bytes);
     }
     free(r);
+    close(fd);
     return 0;
 }

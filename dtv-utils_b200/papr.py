@@ -62,7 +62,8 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_shard_counts_async", "papr_shard_finish", "papr_multi_create", "papr_multi_destroy",
                "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
                "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain",
-               "papr_xchg_export", "papr_xchg_attach", "papr_xchg_detach", "papr_shard_analyze_p2p"]
+               "papr_xchg_export", "papr_xchg_attach", "papr_xchg_detach", "papr_shard_analyze_p2p",
+               "papr_analyze_fd", "papr_multi_analyze_fd"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -89,6 +90,8 @@ def load_library(path: Optional[str] = None):
     lib.papr_analyze_host.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
     lib.papr_analyze_device.argtypes = [vp, vp, u64, i32, C.POINTER(PaprResult)]
     lib.papr_analyze_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(PaprResult)]
+    lib.papr_analyze_fd.argtypes = [vp, i32, i32, C.POINTER(PaprResult)]
+    lib.papr_multi_analyze_fd.argtypes = [vp, i32, i32, C.POINTER(PaprResult)]
     lib.papr_stats_device.argtypes = [vp, vp, u64, u64, C.POINTER(PaprStats)]
     lib.papr_stats_host.argtypes = [vp, vp, u64, u64, C.POINTER(PaprStats), C.POINTER(vp), C.POINTER(u64)]
     lib.papr_stats_merge.argtypes = [C.POINTER(PaprStats), C.POINTER(PaprStats)]
@@ -246,6 +249,12 @@ class Engine:
         res = PaprResult()
         self._check(self.lib.papr_analyze_file(self.h, os.fsencode(path), int(bool(graph)), C.byref(res)),
                     "papr_analyze_file")
+        return res
+
+    def analyze_fd(self, fd: int, graph: bool = False) -> PaprResult:
+        """An open descriptor: a regular file, or a pipe / FIFO (read once, streamed to the GPU as it arrives)."""
+        res = PaprResult()
+        self._check(self.lib.papr_analyze_fd(self.h, fd, int(bool(graph)), C.byref(res)), "papr_analyze_fd")
         return res
 
     # stages (sharded callers) --------------------------------------------------------------------

@@ -122,8 +122,12 @@ int papr_analyze_host(papr_engine *e, const void *file_image, uint64_t file_byte
 int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t nsamples, int graph,
                         papr_result *out);
 /* The same for a file: regular files are read with pread() straight into the pinned staging ring
- * (no mapping); FIFOs and other streams are read to the end first (no seek needed, unlike papr.c:142). */
+ * (no mapping).  FIFOs, pipes and other non-seekable inputs - which the reference cannot read at all, it
+ * rewinds its file (papr.c:142) - are read ONCE: each piece goes from read(2) through a pinned slot to the
+ * GPU while pass 1 runs on the chunks already there, and the chunks stay resident for the CCDF pass (the
+ * stream must fit the GPU's free memory).  papr_analyze_fd takes an open descriptor (not closed). */
 int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out);
+int papr_analyze_fd(papr_engine *e, int fd, int graph, papr_result *out);
 
 /* ---- one capture over several GPUs of this box (single process) --------------------------------- */
 /* Byte-range shards (whole 64 MiB chunks), one engine and one host thread per GPU; pass-1 states
@@ -139,6 +143,7 @@ int  papr_multi_set(papr_multi *m, const char *name, double value);       /* pap
 int  papr_multi_analyze_host(papr_multi *m, const void *file_image, uint64_t file_bytes, int graph,
                              papr_result *out);
 int  papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out);
+int  papr_multi_analyze_fd(papr_multi *m, int fd, int graph, papr_result *out); /* a pipe is read by the first GPU */
 const char *papr_multi_last_error(const papr_multi *m);
 const char *papr_multi_exchange(const papr_multi *m); /* "nccl" or why the host summed the counts */
 

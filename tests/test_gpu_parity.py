@@ -461,3 +461,51 @@ def test_sum_chain_declines_rather_than_guessing(built, eng, torch_cuda):
     finally:
         eng.set("predict_bias", 1.0)
         eng.set("mode", 0)
+
+
+# ---- non-seekable inputs: the reference needs a seekable file (papr.c:142), the drop-in does not -----------
+def _feed(path_or_fd, img, piece=1 << 16):
+    import threading
+
+    def run():
+        with (open(path_or_fd, "wb") if isinstance(path_or_fd, str) else os.fdopen(path_or_fd, "wb")) as f:
+            for k in range(0, len(img), piece):
+                f.write(img[k:k + piece])
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    return t
+
+
+@pytest.mark.parametrize("name", ["appA_1M", "odd_floats_short", "odd_floats_long", "odd_bytes_even", "odd_bytes_odd", "odd_bytes_short",
+                                  "exact_chunks", "ties", "nan", "neg_nan_q", "empty", "one_sample", "zeros_1000"])
+def test_fifo_and_stdin_are_streamed(built, eng, name, manifest, tmp_path):
+    """A named FIFO on the command line and `papr /dev/stdin < file` (a pipe): same text as the reference prints
+    for the same bytes in a regular file - including the lone-I / stale-Q tail, which needs the last 128 KiB of
+    a stream whose length is unknown until it ends.  The FIFO is opened exactly once (a writer that sees its
+    reader vanish gets SIGPIPE / EPIPE)."""
+    if name not in fixtures.FIXTURES:
+        pytest.skip("no such fixture")
+    img = fixtures.image(name)
+    for graph in (False, True):
+        want = _gold(name, graph)
+        fifo = str(tmp_path / ("in_%d.fifo" % graph))
+        os.mkfifo(fifo)
+        t = _feed(fifo, img)
+        r = subprocess.run([built.cli_path()] + (["-g"] if graph else []) + [fifo], capture_output=True, timeout=120)
+        t.join(30)
+        assert r.returncode == 0 and r.stderr == b"" and r.stdout == want, (name, graph, r.stderr[-300:])
+        p = subprocess.Popen([built.cli_path()] + (["-g"] if graph else []) + ["/dev/stdin"], stdin=subprocess.PIPE,
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        out, err = p.communicate(img, timeout=120)
+        assert p.returncode == 0 and err == b"" and out == want, (name, graph)
+    # through the C ABI with small chunks: many device chunks, the tail sample in a chunk of its own
+    eng.set("chunk_bytes", 1 << 20)
+    try:
+        rd, wr = os.pipe()
+        t = _feed(wr, img)
+        res = eng.analyze_fd(rd, False)
+        os.close(rd)
+        t.join(30)
+        assert built.format_result(res) == _gold(name, False)
+    finally:
+        eng.set("chunk_bytes", 64 << 20)
