@@ -243,6 +243,8 @@ void papr_launch_xt_chain_x(const PaprSuperRec *hyper, const PaprSuperRec *super
                             unsigned long long seq, cudaStream_t s);
 void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
                           unsigned long long seq, cudaStream_t s);
+void papr_launch_tr(float *x, int nsym, int n, const float *kernel, const int *tone, int ntones, float vclip, int iterations,
+                    float amax, float *r_out, int *iters_out, int grid, cudaStream_t s);
 int papr_scan_tma_configure(void);
 void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, const PaprScanArgs &a, const PaprExactArgs &x,
                           cudaStream_t s);

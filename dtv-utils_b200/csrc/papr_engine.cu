@@ -90,6 +90,7 @@ std::string g_create_error;
 struct HostSource {
     const unsigned char *img = nullptr;
     int fd = -1;
+    int dfd = -1;  // the same file opened with O_DIRECT (tunable "o_direct"): aligned pieces bypass the page cache
     u64 base = 0;  // file offset of byte 0 of this source (shards of one file)
     u64 bytes = 0;
     bool pinned = false;
@@ -105,6 +106,19 @@ struct HostSource {
         if (img) { memcpy(dst, img + off, len); return true; }
         off += base;
         char *d = (char *)dst;
+        if (dfd >= 0 && ((off | len | (u64)(uintptr_t)dst) & 4095) == 0) { // straight from the device into the pinned slot
+            u64 o = off;
+            size_t l = len;
+            char *q = d;
+            while (l) {
+                ssize_t got = pread(dfd, q, l, (off_t)o);
+                if (got < 0 && errno == EINTR) continue;
+                if (got <= 0 || (got & 4095)) break; // not supported here after all / short read: the buffered descriptor finishes
+                q += got; o += (u64)got; l -= (size_t)got;
+            }
+            if (l == 0) return true;
+            d = q; off = o; len = l;
+        }
         while (len) {
             ssize_t got = pread(fd, d, len, (off_t)off);
             if (got < 0 && errno == EINTR) continue;
@@ -212,6 +226,7 @@ struct papr_engine {
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
+    int o_direct = 0;         // 1: regular files are also opened with O_DIRECT (NVMe -> pinned staging, no page cache)
     int exact_sum = -1;       // != 0 (default): the reference's sequential double sum, bit for bit, on every path; 0: off
     // exact sequential-sum scratch (grown on demand)
     u64 seq_tiles = 0;
@@ -423,6 +438,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
     else if (n == "exact_sum") e->exact_sum = (int)v;
+    else if (n == "o_direct") e->o_direct = v != 0;
     else if (n == "fine_bytes_log2") // <= the allocation, >= two slots of the finest cell size (u64 per float32 value)
         e->fine_bytes_log2 = std::min(26, std::max(3 + PAPR_SH_MIN + 1, (int)v));
     else if (n == "xchg_timeout_s") {
@@ -1391,6 +1407,23 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     return PAPR_OK;
 }
 
+// tone-reservation PAPR reduction of nsym time-domain OFDM symbols of fft_size samples each, in place (papr_tr.cu)
+extern "C" int papr_tr_reduce_device(papr_engine *e, float *d_symbols, int nsym, int fft_size, const float *d_kernel,
+                                     const int *d_tones, int ntones, float vclip, int iterations, float amax,
+                                     float *d_tone_values, int *d_iterations)
+{
+    if (!e || !d_symbols || !d_kernel || !d_tones || !d_tone_values || nsym < 0 || fft_size < 2 || ntones < 1 || iterations < 0)
+        return PAPR_ERR_ARG;
+    if (!(vclip > 0.f) || !(amax >= 0.f)) return fail(e, PAPR_ERR_ARG, "vclip must be positive and amax non-negative");
+    cudaSetDevice(e->device);
+    if (nsym == 0) return PAPR_OK;
+    papr_launch_tr(d_symbols, nsym, fft_size, d_kernel, d_tones, ntones, vclip, iterations, amax, d_tone_values, d_iterations,
+                   std::min(nsym, e->num_sms * 2), e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return PAPR_OK;
+}
+
 extern "C" int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first, uint64_t n, uint64_t seed)
 {
     if (!e || (n && !d_iq)) return PAPR_ERR_ARG;
@@ -2010,6 +2043,13 @@ static int analyze_stream(papr_engine *e, int fd, int graph, papr_result *out)
     return PAPR_OK;
 }
 
+static int reopen_direct(int fd)
+{
+    char p[64];
+    snprintf(p, sizeof(p), "/proc/self/fd/%d", fd);
+    return ::open(p, O_RDONLY | O_DIRECT);
+}
+
 // The capture behind a file descriptor: a regular file is read with pread() chunk by chunk (page cache ->
 // pinned staging, no mapping); anything else is streamed once (analyze_stream).
 extern "C" int papr_analyze_fd(papr_engine *e, int fd, int graph, papr_result *out)
@@ -2023,7 +2063,10 @@ extern "C" int papr_analyze_fd(papr_engine *e, int fd, int graph, papr_result *o
     src.fd = fd;
     src.bytes = (u64)sb.st_size;
     posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-    return analyze_source(e, src, graph, out);
+    src.dfd = e->o_direct ? reopen_direct(fd) : -1; // (tmpfs and some overlays refuse O_DIRECT: buffered reads then)
+    const int rc = analyze_source(e, src, graph, out);
+    if (src.dfd >= 0) ::close(src.dfd);
+    return rc;
 }
 
 extern "C" int papr_analyze_file(papr_engine *e, const char *path, int graph, papr_result *out)
@@ -2360,7 +2403,10 @@ extern "C" int papr_multi_analyze_fd(papr_multi *m, int fd, int graph, papr_resu
     src.fd = fd;
     src.bytes = (u64)sb.st_size;
     posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-    return multi_analyze_source(m, src, graph, out);
+    src.dfd = m->eng[0]->o_direct ? reopen_direct(fd) : -1;
+    const int rc = multi_analyze_source(m, src, graph, out);
+    if (src.dfd >= 0) ::close(src.dfd);
+    return rc;
 }
 
 extern "C" int papr_multi_analyze_file(papr_multi *m, const char *path, int graph, papr_result *out)

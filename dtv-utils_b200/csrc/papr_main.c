@@ -93,6 +93,7 @@ int papr_main(int argc, char **argv)
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_multi_set(m, "chunk_bytes", atof(v) * 1048576.0);
         if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_multi_set(m, "staging_threads", atof(v));
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_multi_set(m, "exact_sum", atof(v));
+        if ((v = getenv("PAPR_B200_ODIRECT"))) papr_multi_set(m, "o_direct", atof(v));
         int rc = papr_multi_analyze_fd(m, fd, graph, r);
         if (rc != PAPR_OK) {
             fprintf(stderr, "papr: %s\n", papr_multi_last_error(m));
@@ -119,6 +120,7 @@ int papr_main(int argc, char **argv)
         if ((v = getenv("PAPR_B200_CHUNK_MB"))) papr_engine_set(e, "chunk_bytes", atof(v) * 1048576.0);
         if ((v = getenv("PAPR_B200_STAGING_THREADS"))) papr_engine_set(e, "staging_threads", atof(v));
         if ((v = getenv("PAPR_B200_EXACT_SUM"))) papr_engine_set(e, "exact_sum", atof(v)); /* default: on for files */
+        if ((v = getenv("PAPR_B200_ODIRECT"))) papr_engine_set(e, "o_direct", atof(v)); /* NVMe -> pinned staging, no page cache */
         if ((v = getenv("PAPR_B200_MAX_RESIDENT_MB"))) papr_engine_set(e, "max_resident_bytes", atof(v) * 1048576.0);
         const double t1 = now_ms();
         int rc = papr_analyze_fd(e, fd, graph, r);

@@ -63,7 +63,7 @@ ABI_SYMBOLS = ["papr_abi_version", "papr_engine_create", "papr_engine_destroy", 
                "papr_multi_set", "papr_multi_analyze_host", "papr_multi_analyze_file", "papr_multi_last_error",
                "papr_multi_exchange", "papr_seqsum_prepare", "papr_seqsum_runs", "papr_seqsum_chain",
                "papr_xchg_export", "papr_xchg_attach", "papr_xchg_detach", "papr_shard_analyze_p2p",
-               "papr_analyze_fd", "papr_multi_analyze_fd"]
+               "papr_analyze_fd", "papr_multi_analyze_fd", "papr_tr_reduce_device"]
 BUF_PRESAMPLE, BUF_LOCAL_STATS, BUF_COUNTS = 0, 1, 2
 
 
@@ -106,6 +106,7 @@ def load_library(path: Optional[str] = None):
     lib.papr_format.restype = C.c_long
     lib.papr_result_finish.argtypes = [C.POINTER(PaprResult), i32]
     lib.papr_siggen_device.argtypes = [vp, vp, u64, u64, u64]
+    lib.papr_tr_reduce_device.argtypes = [vp, vp, i32, i32, vp, vp, i32, C.c_float, i32, C.c_float, vp, vp]
     lib.papr_engine_device_buffer.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
     lib.papr_shard_presample_async.argtypes = [vp, vp, u64, i32]
     lib.papr_shard_scan_async.argtypes = [vp, vp, u64, u64, i32, i32]
@@ -365,6 +366,22 @@ class Engine:
         res = PaprResult()
         rc = self._check(self.lib.papr_shard_finish(self.h, int(bool(graph)), C.byref(res)), "papr_shard_finish")
         return rc == 1, res
+
+    def tr_reduce(self, symbols, kernel, tones, vclip: float = 3.3, iterations: int = 3, amax: float = 1e30):
+        """Tone-reservation PAPR reduction (papr_tr_reduce_device) of `symbols` ([nsym, N] complex64 CUDA tensor,
+        corrected in place) with reference kernel `kernel` ([N] complex64) and reserved carriers `tones`.
+        Returns (reserved-tone values [nsym, ntones] complex64, iterations [nsym] int32)."""
+        import torch
+        nsym, n = symbols.shape
+        tn = torch.as_tensor(tones, dtype=torch.int32, device=symbols.device).contiguous()
+        r = torch.empty((nsym, tn.numel()), dtype=torch.complex64, device=symbols.device)
+        it = torch.empty(nsym, dtype=torch.int32, device=symbols.device)
+        assert symbols.is_contiguous() and symbols.dtype == torch.complex64 and kernel.dtype == torch.complex64
+        torch.cuda.synchronize()
+        self._check(self.lib.papr_tr_reduce_device(self.h, symbols.data_ptr(), nsym, n, kernel.data_ptr(), tn.data_ptr(),
+                                                   tn.numel(), float(vclip), int(iterations), float(amax), r.data_ptr(),
+                                                   it.data_ptr()), "papr_tr_reduce_device")
+        return r, it
 
     def siggen(self, d_out, first_index: int, nsamples: int, seed: int):
         self._check(self.lib.papr_siggen_device(self.h, _ptr(d_out), first_index, nsamples, seed),

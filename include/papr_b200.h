@@ -99,7 +99,9 @@ void *papr_engine_stream(papr_engine *e);
  * (default 0 = what the GPU has free, less 1 GiB) are not kept resident in HBM but streamed twice,
  * like the reference reads its file twice (papr.c:142); "exact_sum": != 0 (default) = emulate the reference's sequential
  * double sum (papr.c:104) bit for bit on every path - inside the fused sweep for large device-resident shards
- * (papr_result.sum_path says which way), 0 = any fixed summation order; "xchg_timeout_s": how long the in-kernel
+ * (papr_result.sum_path says which way), 0 = any fixed summation order; "o_direct": 1 = regular files are also opened with O_DIRECT and every
+ * 4096-byte-aligned piece is read straight into the pinned staging slots, bypassing the page cache (silently buffered
+ * where the file system refuses O_DIRECT, e.g. tmpfs); "xchg_timeout_s": how long the in-kernel
  * peer exchange waits for a rank before ALL ranks give up (default 30)).  Returns PAPR_ERR_ARG for an unknown name. */
 int  papr_engine_set(papr_engine *e, const char *name, double value);
 
@@ -225,6 +227,18 @@ int papr_seqsum_chain(papr_engine *e, const float *d_iq, uint64_t nsamples, doub
 long papr_format(const papr_result *r, char *out, size_t cap);
 /* Fill avg/papr/levels of `r` from r->stats (papr_levels) — for callers that merged shards. */
 int papr_result_finish(papr_result *r, int graph);
+
+/* ---- PAPR reduction by tone reservation --------------------------------- */
+/* What `dtv.dvbt2_paprtr_cc(..., vclip, iterations, fftsize)` of the reference's DVB-T2 chain does
+ * (dvbt2-blade.py:52-54,129; the block is GNU Radio gr-dtv's, the algorithm EN 302 755 clause 9.6.2.1), on
+ * nsym time-domain symbols of fft_size complex samples held at d_symbols (corrected in place):
+ * d_kernel = the reference kernel p (fft_size complex: IFFT of 1 on every reserved tone, p[0] = 1),
+ * d_tones = the reserved carrier indices (FFT bin numbers), amax = bound on what one reserved tone may
+ * carry.  d_tone_values (nsym x ntones complex) receives the reserved tones' values in the kernel's
+ * normalisation, d_iterations (nsym ints, may be NULL) the iterations each symbol took. */
+int papr_tr_reduce_device(papr_engine *e, float *d_symbols, int nsym, int fft_size, const float *d_kernel,
+                          const int *d_tones, int ntones, float vclip, int iterations, float amax,
+                          float *d_tone_values, int *d_iterations);
 
 /* ---- synthetic captures (SURVEY.md Appendix A generator, bit-identical to its C/numpy twins) -- */
 int papr_siggen_device(papr_engine *e, float *d_iq, uint64_t first_index, uint64_t nsamples,

@@ -509,3 +509,20 @@ def test_fifo_and_stdin_are_streamed(built, eng, name, manifest, tmp_path):
         assert built.format_result(res) == _gold(name, False)
     finally:
         eng.set("chunk_bytes", 64 << 20)
+
+
+def test_o_direct_reads_give_the_same_answer(built, eng, manifest, tmp_path):
+    """tunable "o_direct": regular files are read with O_DIRECT straight into the pinned staging slots where the
+    file system allows it (silently buffered where it does not, e.g. tmpfs) - same text either way, including a
+    file whose length is not a multiple of the 4096-byte alignment O_DIRECT needs."""
+    eng.set("o_direct", 1)
+    eng.set("chunk_bytes", 1 << 20)
+    try:
+        for name in ("appA_1M", "odd_bytes_odd", "exact_chunks"):
+            p = tmp_path / (name + ".cfile")
+            p.write_bytes(fixtures.image(name))
+            for graph in (False, True):
+                assert built.format_result(eng.analyze_file(str(p), graph)) == _gold(name, graph)
+    finally:
+        eng.set("o_direct", 0)
+        eng.set("chunk_bytes", 64 << 20)
