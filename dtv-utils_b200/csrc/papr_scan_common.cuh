@@ -103,6 +103,13 @@ __device__ __forceinline__ unsigned hist_bump(unsigned addr)
     return fb;
 }
 
+// one more per-value counter, predicated (no branch): fb = 1 + first fine-table counter of the sample's cell, 0 = none
+__device__ __forceinline__ void fine_bump(unsigned long long *g_fine, unsigned fb, unsigned bits, unsigned fmask)
+{
+    unsigned long long *p = g_fine + (fb - 1u + (bits & fmask)); // (never dereferenced when fb == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.global.add.u64 [%1], 1;\n\t}" ::"r"(fb), "l"(p) : "memory");
+}
+
 // the two samples of one 16-byte load
 template <bool STATS, bool HIST>
 __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, float v1)
@@ -111,8 +118,8 @@ __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, 
     const unsigned f0 = hist_bump(hist_slot(st, b0));
     const unsigned f1 = hist_bump(hist_slot(st, b1));
     if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
-        if (f0) atomicAdd(&st.g_fine[f0 - 1u + (b0 & st.fmask)], 1ull);
-        if (f1) atomicAdd(&st.g_fine[f1 - 1u + (b1 & st.fmask)], 1ull);
+        fine_bump(st.g_fine, f0, b0, st.fmask);
+        fine_bump(st.g_fine, f1, b1, st.fmask);
     }
 }
 
