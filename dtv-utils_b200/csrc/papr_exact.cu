@@ -152,6 +152,16 @@ __device__ __forceinline__ unsigned xt_locate(const float4 (&r)[XT_RUN / 2], int
     return __reduce_min_sync(FULL, pos);
 }
 
+// smallest power a sample needs to have a chance against any of the five records (see the sweep)
+__device__ __forceinline__ float xt_threshold(const int (&val)[PAPR_NTRACK])
+{
+    float m = __int_as_float(val[TR_RE_POS]);
+    m = fminf(m, __int_as_float(val[TR_RE_NEG]));
+    m = fminf(m, __int_as_float(val[TR_IM_POS]));
+    m = fminf(m, __int_as_float(val[TR_IM_NEG])); // magnitudes (>= 0); 0 = no sample of that sign yet: every batch passes
+    return __fmul_rd(m, m);
+}
+
 __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                       const PaprScanArgs a, const PaprExactArgs x)
 {
@@ -204,6 +214,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
     const unsigned tstride = gridDim.x * XT_WARPS;
     unsigned phase = 0;
     double wsum = 0.0; // lane 0: approximate sum of this warp's tiles (what the tree sum used to be)
+    float thr = xt_threshold(st.run_val);
 
     unsigned tile = blockIdx.x * XT_WARPS + warp;
     if (tile < ntiles) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 32), bar);
@@ -251,25 +262,30 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
                 }
             }
 
-            // ---- power and extremes (papr.c:103,105-126)
+            // ---- power and extremes (papr.c:103,105-126).  One conservative test covers all five trackers: a sample
+            //      can raise a component record r only if I^2 or Q^2 >= r^2, hence only if its power >= thr = the
+            //      smallest squared component record (rounded down) - and the peak record is never below thr.  The
+            //      chance of a batch passing falls like 1/(samples seen), the same as that of a real update.
             float v[XT_RUN];
             {
-                float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
+                float vm = 0.f;
 #pragma unroll
                 for (int u = 0; u < XT_RUN / 2; ++u) {
-                    const float4 q = r[u];
-                    v[2 * u] = power_of(q.x, q.y);
-                    v[2 * u + 1] = power_of(q.z, q.w);
-                    bm0 = fmaxf(bm0, fmaxf(v[2 * u], v[2 * u + 1]));
-                    bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
-                    bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
-                    bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
-                    bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
+                    v[2 * u] = power_of(r[u].x, r[u].y);
+                    v[2 * u + 1] = power_of(r[u].z, r[u].w);
+                    vm = fmaxf(vm, fmaxf(v[2 * u], v[2 * u + 1])); // (drops NaN operands, like the reference's compares)
                 }
-                const bool cand = __float_as_int(bm0) > st.run_val[TR_PEAK] || __float_as_int(bm1) > st.run_val[TR_RE_POS] ||
-                                  __float_as_int(bm2) > st.run_val[TR_RE_NEG] || __float_as_int(bm3) > st.run_val[TR_IM_POS] ||
-                                  __float_as_int(bm4) > st.run_val[TR_IM_NEG];
-                if (__any_sync(FULL, cand)) { // warp-uniform and rare after the first few batches
+                if (__any_sync(FULL, vm >= thr)) { // warp-uniform and rare after the first few batches
+                    float bm0 = 0.f, bm1 = 0.f, bm2 = 0.f, bm3 = 0.f, bm4 = 0.f;
+#pragma unroll
+                    for (int u = 0; u < XT_RUN / 2; ++u) {
+                        const float4 q = r[u];
+                        bm0 = fmaxf(bm0, fmaxf(v[2 * u], v[2 * u + 1]));
+                        bm1 = fmaxf(bm1, fmaxf(q.x, q.z));
+                        bm2 = fmaxf(bm2, fmaxf(-q.x, -q.z));
+                        bm3 = fmaxf(bm3, fmaxf(q.y, q.w));
+                        bm4 = fmaxf(bm4, fmaxf(-q.y, -q.w));
+                    }
                     const unsigned batch_off = (b_first + b) * XT_BATCH_SAMPLES;
                     const float bm[PAPR_NTRACK] = {bm0, bm1, bm2, bm3, bm4};
 #pragma unroll
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
                             if (lane == 0) { s_val[t][warp] = w; s_pos[t][warp] = batch_off + pos; }
                         }
                     }
+                    thr = xt_threshold(st.run_val);
                 }
             }
             // the batch is in registers: fetch the next one of this tile, or the first one of this warp's next tile
