@@ -108,6 +108,7 @@ struct PaprScanArgs {
 #define XT_SUPER_SAMPLES (XT_SUPER_TILES * XT_TILE_SAMPLES)
 #define XT_HYPER_SUPERS 32                                     // super-tiles per hyper-tile record (4M samples)
 #define XT_HYPER_SAMPLES ((unsigned long long)XT_HYPER_SUPERS * XT_SUPER_SAMPLES)
+#define XT_NCELLS PAPR_NCELLS_MAX                              // cells of the TMA-fed sweep's histogram
 #define XT_MAX_CAND 4                                          // candidate binades of a multi tile
 #define XT_KBIAS 1100                                          // tile code: k + XT_KBIAS in bits 0-11 ...
 #define XT_CODE_NC(c) (((c) >> 12) & 7)                        // ... candidates in bits 12-14 (0 = none) ...
@@ -210,7 +211,8 @@ void papr_launch_presample(const float *iq, unsigned long long nsamples, int str
                            double *cta_pre /* [grid*3] */, cudaStream_t s);
 void papr_launch_presample_reduce(const double *cta_pre, int nctas, double *pre4, cudaStream_t s);
 void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas,
-                           float bias, int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
+                           float bias, int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s,
+                           int ncells_max = PAPR_NCELLS_MAX);
 void papr_launch_plan_exact(const PaprDevLevels *lv, const PaprDevStats *merged, int fine_bytes_log2,
                             PaprPlan *plan, unsigned *fine_base, cudaStream_t s);
 void papr_launch_zero_fine(const PaprPlan *plan, unsigned long long *g_fine, int grid, cudaStream_t s);
@@ -232,7 +234,8 @@ void papr_launch_seqsum(const float *iq, unsigned long long nsamples, const shor
                         void *tile_run /* {double e0, e1}[ntiles] */, int grid, cudaStream_t s);
 int papr_seqsum_configure(void);
 void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
-                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, unsigned long long seq, cudaStream_t s);
+                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, unsigned long long seq, cudaStream_t s,
+                             int ncells_max = PAPR_NCELLS_MAX);
 void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
                                    unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,

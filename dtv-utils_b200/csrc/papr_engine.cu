@@ -1032,7 +1032,8 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
         papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES), stride,
                               e->grid, e->d_pre_cta, e->stream);
         papr_launch_plan_pred(nullptr, e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas, e->predict_bias,
-                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream);
+                              1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->stream,
+                              chained ? XT_NCELLS : PAPR_NCELLS_MAX);
         papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
         e->launches += 3;
         if (chained) {
@@ -1342,17 +1343,17 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     int rc;
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
-    papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
-                          presample_stride_for(e, n, graph), e->grid, e->d_pre_cta, e->stream);
-    papr_launch_plan_pred_x(e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas, e->predict_bias,
-                            1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->peers,
-                            ++e->xseq[XK_PRE], e->stream);
-    papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
-    e->launches += 3;
     // the sequential sum inside the sweep: all ranks must agree on taking this path (same n is not required, the
     // tunable and the minimum size are): every rank then runs the chain exchange
     const bool chained = xt_applicable(e, n);
     e->xt_status = -1;
+    papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
+                          presample_stride_for(e, n, graph), e->grid, e->d_pre_cta, e->stream);
+    papr_launch_plan_pred_x(e->d_pre_cta, e->grid, e->tables(graph), e->window_sigmas, e->predict_bias,
+                            1 << (e->fine_bytes_log2 - 3 - PAPR_SH_MIN), &e->d_out->plan, e->d_fine_base, e->peers,
+                            ++e->xseq[XK_PRE], e->stream, chained ? XT_NCELLS : PAPR_NCELLS_MAX);
+    papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
+    e->launches += 3;
     if (chained) {
         if ((rc = enqueue_scan_tma(e, d_iq, n, first, true))) return rc;
         const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
@@ -1782,6 +1783,7 @@ static int analyze_source(papr_engine *e, const HostSource &src, int graph, papr
     CU(cudaEventRecord(e->ev_begin, e->stream));
     bool exact_done = false;
     if ((rc = host_pass1(e, src, g, resident, e->exact_sum != 0 ? SEQ_FULL : SEQ_NONE, &exact_done))) return rc;
+    out->sum_path = exact_done ? 3u : 0u;
     mark("H2D + pass 1 (+ exact sum)");
     // local state -> merged state, avg, L, levels on the device
     papr_launch_levels(&e->d_out->local, 1, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,

@@ -111,11 +111,12 @@ __device__ __forceinline__ int xt_candidates(double avg, double window, double w
 // the fused scan
 // ------------------------------------------------------------------------------------------------
 #ifndef XT_THREADS
-#define XT_THREADS 640 // 20 warps x 4 KiB in flight; ~100 registers per thread
+#define XT_THREADS 640 // 20 warps x 4 KiB in flight; ~100 registers per thread (24 warps: more spills than gain, profiles/README.md)
 #endif
 #define XT_WARPS (XT_THREADS / 32)
 #define XT_RING_BYTES (XT_WARPS * 4096)
-#define XT_SMEM_BYTES (SCAN_SMEM_BYTES + 1024 + XT_RING_BYTES)
+#define XT_HIST_BYTES (8 * (XT_NCELLS + 2))
+#define XT_SMEM_BYTES (XT_HIST_BYTES + 1024 + XT_RING_BYTES)
 
 // entry parity of this lane's run given the exit parities of the lower lanes (b0 / b1: ballots of the exit
 // parity for an even / odd entry) and the parity P with which the batch is entered
@@ -178,13 +179,13 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
     const PaprPlan pl = *a.plan;
     const bool do_hist = (pl.status & PLAN_HIST) != 0;
     {
-        unsigned *s_fb = s_hist + (PAPR_NCELLS_MAX + 2);
+        unsigned *s_fb = s_hist + (XT_NCELLS + 2);
         st.g_fine = a.g_fine;
         asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
                      : "=r"(st.smem_slot1) : "l"(s_hist + 1));
         st.sh = pl.sh;
         st.cell_base = do_hist ? pl.cell_base : 0x7fffffff; // no valid plan: every sample lands in slot 0
-        st.ncells = do_hist ? pl.ncells : 0;
+        st.ncells = do_hist ? min(pl.ncells, XT_NCELLS) : 0;
         st.fmask = (1u << pl.sh) - 1u;
         for (int i = threadIdx.x; i < st.ncells + 2; i += XT_THREADS) {
             s_hist[i] = 0;
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
         st.run_val[t] = a.wp[blockIdx.x].val[t]; // carried over from earlier launches of this shard
         if (lane == 0) { s_val[t][warp] = 0; s_pos[t][warp] = 0xffffffffu; }
     }
-    const unsigned ring = (smem_u32(scan_smem) + SCAN_SMEM_BYTES + 1023u) & ~1023u;
+    const unsigned ring = (smem_u32(scan_smem) + XT_HIST_BYTES + 1023u) & ~1023u;
     const unsigned my = ring + (unsigned)warp * 4096u, bar = smem_u32(&s_bar[warp]);
     if (lane == 0) mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
 
             // ---- CCDF cells (papr.c:147-151)
 #pragma unroll
-            for (int u = 0; u < XT_RUN / 2; ++u) hist_pair(st, v[2 * u], v[2 * u + 1]);
+            for (int u = 0; u < XT_RUN / 2; ++u) hist_pair<true, true, 4 * (XT_NCELLS + 2)>(st, v[2 * u], v[2 * u + 1]);
 
             // ---- papr.c:104
             if (nc == 1) {
@@ -648,6 +649,8 @@ __device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList
     __shared__ double s_xp[XT_MAX_CROSS];
     __shared__ unsigned s_xt[XT_MAX_XTILES];   // crossing tiles
     __shared__ double s_xtp[XT_MAX_XTILES];
+    __shared__ int s_xtc[XT_MAX_XTILES];       // ... and their codes
+    __shared__ float s_run[XT_CHAIN_T / 32][XT_RUN]; // per warp: the samples of the run in which a crossing happens
     __shared__ unsigned long long s_key[XT_MAX_RAW];
     __shared__ double s_re0[XT_MAX_RAW], s_re1[XT_MAX_RAW]; // the raw items
     __shared__ short s_rk[XT_MAX_RAW];
@@ -846,7 +849,24 @@ __device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList
         }
         if (cross) {
             const int j = atomicAdd(&s_nxt, 1);
-            if (j < XT_MAX_XTILES) { s_xt[j] = tl; s_xtp[j] = pl; } else fail(XW_TOO_MANY_CROSSINGS);
+            if (j < XT_MAX_XTILES) { s_xt[j] = tl; s_xtp[j] = pl; s_xtc[j] = tt.code; } else fail(XW_TOO_MANY_CROSSINGS);
+        }
+        // the samples of a crossing tile will be needed in step 5 (they left L2 long ago): start fetching them now
+        {
+            unsigned xm = __ballot_sync(FULL, cross);
+            while (xm) {
+                const int q = __ffs(xm) - 1;
+                xm &= xm - 1;
+                const unsigned long long s0 = (unsigned long long)(st * XT_SUPER_TILES + q) * XT_TILE_SAMPLES;
+                const int qc = __shfl_sync(FULL, tt.code, q);
+                if (XT_CODE_NC(qc) > 1 && lane < XT_MAX_CAND) // ... and its batch records (128 B per candidate)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(c.multi + ((size_t)XT_CODE_SLOT(qc) * XT_MAX_CAND + lane) * XT_TILE_BATCHES));
+                const char *base = reinterpret_cast<const char *>(c.iq + 2 * s0) + 1024 * lane; // 32 KiB per tile: 1 KiB per lane
+#pragma unroll
+                for (int l = 0; l < 8; ++l)
+                    if (s0 + 128ull * lane + 16ull * l < c.nsamples)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 128 * l));
+            }
         }
         // stretches of ordinary tiles between the boundaries (crossing / literal tiles)
         const unsigned bnd = __ballot_sync(FULL, cross || lit);
@@ -872,7 +892,7 @@ __device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList
     const int nxt = min(s_nxt, XT_MAX_XTILES);
     for (int x = warp; x < nxt; x += XT_CHAIN_T / 32) {
         const unsigned tl = s_xt[x];
-        const int code = c.tile_code[tl], nc = XT_CODE_NC(code), K = XT_CODE_K(code);
+        const int code = s_xtc[x], nc = XT_CODE_NC(code), K = XT_CODE_K(code);
         const int kb = xt_expo(s_xtp[x]), ka = kb + 1;
         if (nc < 2 || kb < K || ka >= K + nc) { if (lane == 0) fail(XW_TILE_NO_CANDIDATE); continue; }
         const PaprTileRun *mb = c.multi + ((size_t)XT_CODE_SLOT(code) * XT_MAX_CAND + (kb - K)) * XT_TILE_BATCHES;
@@ -938,37 +958,37 @@ __device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList
                 emit(XT_IT_SEG, kb, bpos + 2, r.e0, r.e1);
                 emit(XT_IT_SEG, ka, bpos + (unsigned long long)XT_RUN * (lx + 1), q.e0, q.e1);
             }
-            if (lane == lx) {
-                // inside the run: the one sample whose add leaves binade kb is applied literally; the samples
-                // before it form a run in kb, those after it a run in ka (single-sample runs composed in order)
-                double q0 = ql;
-                int jx = -1;
-                PaprTileRun pre, post;
-                pre.e0 = pre.e1 = post.e0 = post.e1 = 0.0;
+            // inside the run: the one sample whose add leaves binade kb is applied literally; the samples before
+            // it form a run in kb, those after it a run in ka.  Lane j takes sample j of the run.
+            if (lane == lx)
 #pragma unroll
-                for (int j = 0; j < XT_RUN; ++j) {
-                    const double d = (double)v[j];
-                    const int kk = jx < 0 ? kb : ka;
-                    PaprTileRun one;
-                    one.e0 = __dsub_rn(__dadd_rn(xt_base(kk, 0), d), xt_base(kk, 0));
-                    one.e1 = __dsub_rn(__dadd_rn(xt_base(kk, 1), d), xt_base(kk, 1));
-                    if (jx < 0 && xt_expo(q0) != xt_expo(q0 + d)) jx = j;
-                    else if (jx < 0) pre = xt_compose(pre, one, kb);
-                    else post = xt_compose(post, one, ka);
-                    q0 += d;
-                }
-                const unsigned long long rpos = bpos + (unsigned long long)XT_RUN * lx;
-                if (jx < 0) fail(XW_LANE_NOT_FOUND);
-                else {
-                    double lit = 0.0;
-#pragma unroll
-                    for (int j = 0; j < XT_RUN; ++j)
-                        if (j == jx) lit = (double)v[j];
-                    emit(XT_IT_SEG, kb, rpos + 3, pre.e0, pre.e1);
-                    emit(XT_IT_LIT, ka, rpos + 4, lit, 0.0);
-                    emit(XT_IT_SEG, ka, rpos + 5, post.e0, post.e1);
-                }
+                for (int j = 0; j < XT_RUN; ++j) s_run[warp][j] = v[j];
+            __syncwarp();
+            const double d = lane < XT_RUN ? (double)s_run[warp][lane] : 0.0;
+            const double qx = __shfl_sync(FULL, ql, lx);
+            const double qs = qx + xt_warp_excl_scan(d, lane, &tot);
+            const unsigned xj = __ballot_sync(FULL, lane < XT_RUN && xt_expo(qs) != xt_expo(qs + d));
+            if (__popc(xj) != 1) { if (lane == 0) fail(XW_LANE_NOT_FOUND); continue; }
+            const int jx = __ffs(xj) - 1;
+            PaprTileRun pre, post;
+            pre.e0 = pre.e1 = post.e0 = post.e1 = 0.0;
+            if (lane < jx) {
+                pre.e0 = __dsub_rn(__dadd_rn(xt_base(kb, 0), d), xt_base(kb, 0));
+                pre.e1 = __dsub_rn(__dadd_rn(xt_base(kb, 1), d), xt_base(kb, 1));
+            } else if (lane > jx && lane < XT_RUN) {
+                post.e0 = __dsub_rn(__dadd_rn(xt_base(ka, 0), d), xt_base(ka, 0));
+                post.e1 = __dsub_rn(__dadd_rn(xt_base(ka, 1), d), xt_base(ka, 1));
             }
+            pre = xt_warp_compose(pre, kb);
+            post = xt_warp_compose(post, ka);
+            const double lit = __shfl_sync(FULL, d, jx);
+            if (lane == 0) {
+                const unsigned long long rpos = bpos + (unsigned long long)XT_RUN * lx;
+                emit(XT_IT_SEG, kb, rpos + 3, pre.e0, pre.e1);
+                emit(XT_IT_LIT, ka, rpos + 4, lit, 0.0);
+                emit(XT_IT_SEG, ka, rpos + 5, post.e0, post.e1);
+            }
+            __syncwarp();
         }
     }
     __threadfence_block();

@@ -444,7 +444,7 @@ __device__ int assign_slots(const unsigned char *s_flag, int ncells, int sh, int
 // Fused mode.  pre4 = {sum, sum of squares, count} of batch sums already reduced over ranks, or
 // (single shard) nctas > 0: fold this GPU's CTA triples here and skip the separate reduce launch.
 __device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, float sigmas, float bias, int fine_slots,
-                               PaprPlan *plan, unsigned *fine_base, int xchg_timeout)
+                               PaprPlan *plan, unsigned *fine_base, int xchg_timeout, int ncells_max)
 {
     __shared__ unsigned char s_flag[PAPR_NCELLS_MAX];
     __shared__ int s_scan[1024];
@@ -470,7 +470,7 @@ __device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, flo
     float lo0 = __double2float_rd(avg * (1.0 - w));
     if (!(lo0 > 0.f)) lo0 = 0.f;
     const int base = (int)(__float_as_uint(lo0) >> sh);
-    const int ncells = PAPR_NCELLS_MAX;
+    const int ncells = min(max(ncells_max, 1024), PAPR_NCELLS_MAX); // (the TMA-fed sweep keeps a smaller histogram)
     for (int c = t; c < PAPR_NCELLS_MAX; c += 1024) s_flag[c] = 0;
     if (t == 0) s_cov = tb.nlevels_max;
     __syncthreads();
@@ -502,7 +502,7 @@ __device__ void plan_pred_body(const double (&pre)[3], const PaprTables &tb, flo
 
 __global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4, const double *cta_pre, int nctas,
                                                               PaprTables tb, float sigmas, float bias, int fine_slots,
-                                                              PaprPlan *plan, unsigned *fine_base)
+                                                              PaprPlan *plan, unsigned *fine_base, int ncells_max)
 {
     double pre[3];
     if (nctas > 0) {
@@ -510,13 +510,13 @@ __global__ void __launch_bounds__(1024) papr_plan_pred_kernel(const double *pre4
     } else {
         pre[0] = pre4[0]; pre[1] = pre4[1]; pre[2] = pre4[2];
     }
-    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, 0);
+    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, 0, ncells_max);
 }
 
 void papr_launch_plan_pred(const double *pre4, const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias,
-                           int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s)
+                           int fine_slots, PaprPlan *plan, unsigned *fine_base, cudaStream_t s, int ncells_max)
 {
-    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base);
+    papr_plan_pred_kernel<<<1, 1024, 0, s>>>(pre4, cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base, ncells_max);
 }
 
 // Exact thresholds known (two-pass mode, or redo after a fused miss): ambiguous = the cells that hold
@@ -642,7 +642,7 @@ void papr_launch_resolve(const PaprPlan *plan, const unsigned *fine_base, const 
 // add them up in rank order (identical on every rank) and plan from the global prediction
 __global__ void __launch_bounds__(1024) papr_plan_pred_x_kernel(const double *cta_pre, int nctas, PaprTables tb,
                                                                 float sigmas, float bias, int fine_slots, PaprPlan *plan,
-                                                                unsigned *fine_base, PaprPeers pp, u64 seq)
+                                                                unsigned *fine_base, PaprPeers pp, u64 seq, int ncells_max)
 {
     __shared__ u64 s_mine[4];
     double pre[3];
@@ -664,13 +664,13 @@ __global__ void __launch_bounds__(1024) papr_plan_pred_x_kernel(const double *ct
         pre[2] += __longlong_as_double((long long)ld_volatile(src + 2));
     }
     if (!ok) pre[2] = 0.0; // no plan: the result is reported as failed anyway
-    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, ok ? 0 : 1);
+    plan_pred_body(pre, tb, sigmas, bias, fine_slots, plan, fine_base, ok ? 0 : 1, ncells_max);
 }
 
 void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
-                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, u64 seq, cudaStream_t s)
+                             PaprPlan *plan, unsigned *fine_base, PaprPeers pp, u64 seq, cudaStream_t s, int ncells_max)
 {
-    papr_plan_pred_x_kernel<<<1, 1024, 0, s>>>(cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base, pp, seq);
+    papr_plan_pred_x_kernel<<<1, 1024, 0, s>>>(cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base, pp, seq, ncells_max);
 }
 
 // sharded: CTA partials -> this shard's pass-1 state -> published; every rank's state collected and

@@ -95,11 +95,13 @@ __device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, 
     return st.smem_slot1 + ((unsigned)d << 2);
 }
 
+// FB_OFF: byte distance from a cell's counter to its fine-table base (the second array of the shared window)
+template <int FB_OFF = 4 * (PAPR_NCELLS_MAX + 2)>
 __device__ __forceinline__ unsigned hist_bump(unsigned addr)
 {
     unsigned fb;
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(fb) : "r"(addr), "n"(4 * (PAPR_NCELLS_MAX + 2)));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(fb) : "r"(addr), "n"(FB_OFF));
     return fb;
 }
 
@@ -111,12 +113,12 @@ __device__ __forceinline__ void fine_bump(unsigned long long *g_fine, unsigned f
 }
 
 // the two samples of one 16-byte load
-template <bool STATS, bool HIST>
+template <bool STATS, bool HIST, int FB_OFF = 4 * (PAPR_NCELLS_MAX + 2)>
 __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, float v1)
 {
     const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
-    const unsigned f0 = hist_bump(hist_slot(st, b0));
-    const unsigned f1 = hist_bump(hist_slot(st, b1));
+    const unsigned f0 = hist_bump<FB_OFF>(hist_slot(st, b0));
+    const unsigned f1 = hist_bump<FB_OFF>(hist_slot(st, b1));
     if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
         fine_bump(st.g_fine, f0, b0, st.fmask);
         fine_bump(st.g_fine, f1, b1, st.fmask);
