@@ -465,8 +465,11 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h // max(e2e_steps, 1), "steps": e2e_steps,
                         "samples_per_gpu": n_host, "host_memory": "pinned",
                         # plain cudaMemcpyAsync of the same pinned buffers, all ranks at once: what the box allows
-                        "h2d_ceiling_gbs_all_ranks": ceil_sum, "h2d_ceiling_gbs_slowest_rank": ceil_min,
-                        "frac_of_h2d_ceiling": (e2e_value * BYTES_PER_SAMPLE / ceil_sum) if (e2e_value and ceil_sum) else None},
+                        # (a step ends when the slowest rank is done, so the ceiling of the synchronised job is
+                        # n_gpus x the slowest rank's rate; the sum of the ranks' own rates is shown beside it)
+                        "h2d_ceiling_gbs_slowest_rank": ceil_min, "h2d_ceiling_gbs_sum_of_ranks": ceil_sum,
+                        "frac_of_h2d_ceiling": (e2e_value * BYTES_PER_SAMPLE / (world * ceil_min)) if (e2e_value and ceil_min) else None,
+                        "frac_of_sum_of_ranks": (e2e_value * BYTES_PER_SAMPLE / ceil_sum) if (e2e_value and ceil_sum) else None},
                 "gpu_launches": m["launches"], "clocks": sampler.result(), "fused_miss": int(res.fused_miss)}
         if subs:
             line["configs"] = subs

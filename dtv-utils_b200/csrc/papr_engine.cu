@@ -222,7 +222,8 @@ struct papr_engine {
     float window_sigmas = 5.0f;
     float predict_bias = 1.0f; // test hook: scales the predicted mean of the fused mode (a wrong one must be caught)
     size_t chunk_bytes = 64u << 20; // H2D + kernel granularity; pageable / file sources are staged in 4 MiB pieces
-    int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16]
+    int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16] (shared among the engines of a papr_multi)
+    int host_share = 1;             // engines of this process that stage from the host at the same time
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
@@ -1466,7 +1467,7 @@ static int ensure_ring(papr_engine *e)
 static int staging_threads_of(const papr_engine *e)
 {
     int n = e->staging_threads;
-    if (n < 0) n = std::min(16, std::max(2, (int)std::thread::hardware_concurrency() - 2));
+    if (n < 0) n = std::min(16, std::max(2, ((int)std::thread::hardware_concurrency() - 2) / std::max(1, e->host_share)));
     return std::min(kMaxStages - 2, std::max(1, n));
 }
 
@@ -2229,6 +2230,7 @@ extern "C" int papr_multi_create(int ndev, const int *devices, papr_multi **out)
             papr_multi_destroy(m);
             return rc;
         }
+        e->host_share = ndev; // the helper threads of all shards share the host's cores and memory bandwidth
         m->eng.push_back(e);
     }
     *out = m;
