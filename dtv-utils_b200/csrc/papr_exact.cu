@@ -69,14 +69,16 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned phase)
 }
 
 // one 4 KiB box: rows [row, row+32) x 128 B of the capture -> swizzled shared memory, completion on `bar`.
-// Called by the whole (converged) warp; one elected lane arms the barrier and issues the copy.
-__device__ __forceinline__ void tma_batch(unsigned dst, const CUtensorMap *tm, int row, unsigned bar)
+// Called by the whole (converged) warp; one elected lane arms the barrier and issues the copy.  Every byte of the
+// capture is used once: the L2 policy `pol` (evict-first) keeps the stream from pushing the fine table, the
+// histogram and the tile records out of L2 (they are what the sweep writes back to DRAM otherwise).
+__device__ __forceinline__ void tma_batch(unsigned dst, const CUtensorMap *tm, int row, unsigned bar, unsigned long long pol)
 {
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "elect.sync _|p, 0xffffffff;\n\t"
                  "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 4096;\n\t"
-                 "@p cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%3, %4}], [%0];\n\t"
-                 "}" ::"r"(bar), "r"(dst), "l"(tm), "r"(0), "r"(row) : "memory");
+                 "@p cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%1], [%2, {%3, %4}], [%0], %5;\n\t"
+                 "}" ::"r"(bar), "r"(dst), "l"(tm), "r"(0), "r"(row), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ float4 lds128(unsigned addr)
@@ -218,7 +220,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
     float thr = xt_threshold(st.run_val);
 
     unsigned tile = blockIdx.x * XT_WARPS + warp;
-    if (tile < ntiles) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 32), bar);
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (tile < ntiles) tma_batch(my, &tmap, (int)(tile * XT_TILE_BATCHES * 32), bar, pol);
     for (; tile < ntiles; tile += tstride) {
         // ---- which binade(s) will the running sum be in while this tile is added?
         const u64 g0 = x.g_first + (u64)tile * XT_TILE_SAMPLES;
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
             __syncwarp();
             {
                 const unsigned nxt = b + 1 < nb ? b_first + b + 1 : (tile + tstride) * XT_TILE_BATCHES;
-                if (nxt < nbatch) tma_batch(my, &tmap, (int)(nxt * 32u), bar);
+                if (nxt < nbatch) tma_batch(my, &tmap, (int)(nxt * 32u), bar, pol);
             }
 
             // ---- CCDF cells (papr.c:147-151)
