@@ -322,24 +322,35 @@ __global__ void __launch_bounds__(PAPR_THREADS, 1) papr_presample_kernel(const f
     const unsigned ngroups = (nbatch + stride - 1) / stride;
     const float4 *p = reinterpret_cast<const float4 *>(iq);
     double s1 = 0.0, s2 = 0.0, cnt = 0.0;
-    for (unsigned g = gw; g < ngroups; g += GW) {
-        unsigned b = g * stride + hash32(g) % stride;
-        if (b >= nbatch) continue;
-        const float4 *q = p + (size_t)b * PAPR_BATCH_VEC + lane;
-        float4 r[PAPR_U];
+    // two groups per trip: 8 independent 16-byte loads in flight per lane (the kernel is latency-bound: a warp
+    // visits only ~14 groups); the batch sums are accumulated in ascending group order, as before
+    for (unsigned g0 = gw; g0 < ngroups; g0 += 2 * GW) {
+        float4 r[2][PAPR_U];
+        bool have[2];
 #pragma unroll
-        for (int u = 0; u < PAPR_U; ++u) r[u] = ldg_stream(q + 32 * u);
-        double ls = 0.0;
+        for (int k4 = 0; k4 < 2; ++k4) {
+            const unsigned g = g0 + k4 * GW;
+            const unsigned b = g < ngroups ? g * stride + hash32(g) % stride : nbatch;
+            have[k4] = b < nbatch;
+            const float4 *q = p + (size_t)(have[k4] ? b : 0) * PAPR_BATCH_VEC + lane;
 #pragma unroll
-        for (int u = 0; u < PAPR_U; ++u) {
-            ls += (double)power_of(r[u].x, r[u].y);
-            ls += (double)power_of(r[u].z, r[u].w);
+            for (int u = 0; u < PAPR_U; ++u) r[k4][u] = have[k4] ? ldg_stream(q + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL, ls, o);
-        s1 += ls;
-        s2 += ls * ls;
-        cnt += 1.0;
+        for (int k4 = 0; k4 < 2; ++k4) {
+            if (!have[k4]) continue; // (warp-uniform)
+            double ls = 0.0;
+#pragma unroll
+            for (int u = 0; u < PAPR_U; ++u) {
+                ls += (double)power_of(r[k4][u].x, r[k4][u].y);
+                ls += (double)power_of(r[k4][u].z, r[k4][u].w);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ls += __shfl_xor_sync(FULL, ls, o);
+            s1 += ls;
+            s2 += ls * ls;
+            cnt += 1.0;
+        }
     }
     __shared__ double s_p[3][PAPR_WARPS];
     const int warp = threadIdx.x >> 5;
