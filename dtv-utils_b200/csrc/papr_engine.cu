@@ -227,6 +227,8 @@ struct papr_engine {
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
+    int p2p_chain = -1;       // sharded in-kernel path: -1 = chain the sequential sum on the device if THIS shard qualifies;
+                              // 0 / 1 = what the ranks agreed on (all must take the same path: papr.py settles it)
     int o_direct = 0;         // 1: regular files are also opened with O_DIRECT (NVMe -> pinned staging, no page cache)
     int exact_sum = -1;       // != 0 (default): the reference's sequential double sum, bit for bit, on every path; 0: off
     // exact sequential-sum scratch (grown on demand)
@@ -440,6 +442,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "fused_min_samples") e->fused_min_samples = (u64)v;
     else if (n == "exact_sum") e->exact_sum = (int)v;
     else if (n == "o_direct") e->o_direct = v != 0;
+    else if (n == "p2p_chain") e->p2p_chain = (int)v;
     else if (n == "fine_bytes_log2") // <= the allocation, >= two slots of the finest cell size (u64 per float32 value)
         e->fine_bytes_log2 = std::min(26, std::max(3 + PAPR_SH_MIN + 1, (int)v));
     else if (n == "xchg_timeout_s") {
@@ -1346,7 +1349,8 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     if ((rc = enqueue_reset(e))) return rc;
     // the sequential sum inside the sweep: all ranks must agree on taking this path (same n is not required, the
     // tunable and the minimum size are): every rank then runs the chain exchange
-    const bool chained = xt_applicable(e, n);
+    const bool chained = e->p2p_chain < 0 ? xt_applicable(e, n) : (e->p2p_chain != 0 && xt_applicable(e, n));
+    if (e->p2p_chain > 0 && !chained) return fail(e, PAPR_ERR_ARG, "p2p_chain = 1 but this shard is too small for the chained sweep");
     e->xt_status = -1;
     papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
                           presample_stride_for(e, n, graph), e->grid, e->d_pre_cta, e->stream);

@@ -102,6 +102,17 @@ for graph in (False, True):
     ok &= struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
     res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2, exact_sum=True)  # and on request for resident ones
     ok &= pb.format_result(res) == want and struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
+# unequal shards, the last one too small for the chained sweep: the ranks agree to leave the device chain out and the
+# sequential sum is supplied stage by stage - same text, same sum bits
+n1 = 5000
+nn = n if rank < world - 1 else n1
+tot = (world - 1) * n + n1
+d2 = torch.empty(2 * nn, dtype=torch.float32, device="cuda")
+eng.siggen(d2, rank * n, nn, 6)
+whole2 = oracle_binding.siggen(0, tot, 6)
+res = pb.analyze_sharded(eng, d2, nn, rank * n, False, mode=2)
+ok &= pb.format_result(res) == oracle_binding.run_image(whole2.tobytes(), False)
+ok &= struct.pack("<d", res.stats.sum) == struct.pack("<d", oracle_binding.analyze(whole2, False)[0].sum)
 print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
 pb.detach_peer_exchange(eng); eng.close()
 dist.barrier(); dist.destroy_process_group()
