@@ -239,11 +239,8 @@ void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, flo
 void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
                                    unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,
-                                   unsigned long long seq, cudaStream_t s, PaprDevStats *parts_out = nullptr);
-void papr_launch_xt_chain_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
-                            const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
-                            const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
-                            unsigned long long seq, cudaStream_t s);
+                                   unsigned long long seq, cudaStream_t s, PaprDevStats *parts_out = nullptr,
+                                   double bias = 1.0 /* test hook: scales the sum the levels are derived from */);
 void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
                           unsigned long long seq, cudaStream_t s);
 void papr_launch_tr(float *x, int nsym, int n, const float *kernel, const int *tone, int ntones, float vclip, int iterations,
@@ -252,9 +249,32 @@ int papr_scan_tma_configure(void);
 void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, const PaprScanArgs &a, const PaprExactArgs &x,
                           cudaStream_t s);
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles,
-                            const PaprTileRun *multi_tile, PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s);
-void papr_launch_xt_chain(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
-                          const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
-                          PaprChainList *out, cudaStream_t s);
+                            const PaprTileRun *multi_tile, PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s,
+                            unsigned long long *zero_word = nullptr /* status word of the counts that follow */);
+// single shard: chain (CTA 0) side by side with finalize + levels + counts from the fixed-order sum (the other CTAs)
+struct PaprEpilogueArgs {
+    const PaprCtaPartial *wp;
+    int nctas;
+    unsigned long long n;
+    PaprTables tb;
+    int graph;
+    double bias;                       // test hook (1.0): scales the sum the speculative levels are derived from
+    PaprDevStats *local, *merged;
+    PaprDevLevels *lv;
+    const PaprPlan *plan;
+    const unsigned *fine_base;
+    const unsigned long long *g_hist, *g_fine, *g_over;
+    unsigned long long *counts, *status_word;
+    int *chain_report;                 // {XT_* status, why}
+    double *chain_exact;               // the chained sequential sum (valid when status == XT_OK)
+};
+// sharded: the chain with its exchange (CTA 0) side by side with this shard's level counts against a.lv (the other CTAs)
+void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
+                               const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
+                               const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
+                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s);
+void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code,
+                             const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles, const float *iq,
+                             unsigned long long nsamples, PaprChainList *out, const PaprEpilogueArgs &a, int grid, cudaStream_t s);
 int papr_scan_smem_bytes(bool hist);
 int papr_scan_configure(void); // sets the dynamic shared-memory attributes once per device

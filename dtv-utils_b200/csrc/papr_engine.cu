@@ -73,7 +73,7 @@ struct DevOut {
     u64 counts[PAPR_MAX_LEVELS + 1]; // [PAPR_MAX_LEVELS] = status word (RES_* bits, summed over ranks)
     PaprDevLevels lv;
     int chain[2];                    // {XT_* status, why} of the sequential sum chained on the device
-    int chain_pad[2];
+    double chain_exact;              // ... and the sum itself (single-shard epilogue; valid when status == XT_OK)
 };
 
 struct HostOut {
@@ -221,6 +221,7 @@ struct papr_engine {
     int presample_stride = 128; // upper bound; see presample_stride_for()
     float window_sigmas = 5.0f;
     float predict_bias = 1.0f; // test hook: scales the predicted mean of the fused mode (a wrong one must be caught)
+    double epilogue_bias = 1.0; // test hook: scales the fixed-order sum the epilogue's speculative levels come from
     size_t chunk_bytes = 64u << 20; // H2D + kernel granularity; pageable / file sources are staged in 4 MiB pieces
     int staging_threads = -1;       // -1: hardware threads - 2, within [2, 16] (shared among the engines of a papr_multi)
     int host_share = 1;             // engines of this process that stage from the host at the same time
@@ -436,6 +437,7 @@ extern "C" int papr_engine_set(papr_engine *e, const char *name, double v)
     else if (n == "presample_stride") e->presample_stride = std::max(1, (int)v);
     else if (n == "window_sigmas") e->window_sigmas = (float)v;
     else if (n == "predict_bias") e->predict_bias = (float)v;
+    else if (n == "epilogue_bias") e->epilogue_bias = v;
     else if (n == "chunk_bytes") e->chunk_bytes = std::max<size_t>(1u << 20, ((size_t)v) & ~(kTileBytes - 1));
     else if (n == "staging_threads") e->staging_threads = std::max(-1, (int)v);
     else if (n == "max_resident_bytes") e->max_resident_bytes = (u64)v;
@@ -571,16 +573,33 @@ static int enqueue_scan_tma(papr_engine *e, const float *d_iq, u64 n, u64 first,
     return PAPR_OK;
 }
 
-// tile runs -> super-tile records -> the chained sum (d_xt_chain[0]: status, exact)
-static int enqueue_xt_chain(papr_engine *e, const float *d_iq, u64 n)
+static PaprEpilogueArgs epilogue_args(papr_engine *e, u64 n, int graph)
+{
+    PaprEpilogueArgs a;
+    a.wp = e->d_work->wp; a.nctas = e->grid; a.n = n;
+    a.tb = e->tables(graph); a.graph = graph; a.bias = e->epilogue_bias;
+    a.local = &e->d_out->local; a.merged = &e->d_out->merged; a.lv = &e->d_out->lv;
+    a.plan = &e->d_out->plan; a.fine_base = e->d_fine_base;
+    a.g_hist = e->d_work->hist; a.g_fine = e->d_fine; a.g_over = &e->d_work->over;
+    a.counts = e->d_out->counts; a.status_word = &e->d_out->counts[PAPR_MAX_LEVELS];
+    a.chain_report = e->d_out->chain; a.chain_exact = &e->d_out->chain_exact;
+    return a;
+}
+
+// single shard, after the TMA-fed sweep: tile runs -> super-tile records, then ONE launch in which CTA 0 chains
+// the sequential sum while the other CTAs do finalize + levels + counts from the fixed-order sum (papr_exact.cu:
+// papr_xt_epilogue_kernel); the host checks the speculative levels against the ones the exact sum gives
+static int enqueue_xt_epilogue(papr_engine *e, const float *d_iq, u64 n, int graph)
 {
     const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
     const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
     const unsigned nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
     papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super, e->d_xt_hyper,
-                           (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
-    papr_launch_xt_chain(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles, d_iq, n,
-                         e->d_xt_chain, e->stream);
+                           (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream,
+                           &e->d_out->counts[PAPR_MAX_LEVELS]);
+    const PaprEpilogueArgs a = epilogue_args(e, n, graph);
+    papr_launch_xt_epilogue(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
+                            d_iq, n, e->d_xt_chain, a, e->num_sms, e->stream);
     e->launches += 2;
     CU(cudaGetLastError());
     return PAPR_OK;
@@ -735,17 +754,18 @@ static int fix_nan_sign(papr_engine *e, const float *d_iq, u64 n, u64 first, pap
     return PAPR_OK;
 }
 
-// Fill `out` from the fetched device results; 1 = device level table disagrees with the host libm
-// (or the fused pass missed): the caller must run the exact CCDF pass with out->level[].
+// Fill `out` from the fetched device results; non-zero = device level table disagrees with the host libm
+// (or the fused pass missed): the caller must count again / run the exact CCDF pass with out->level[].
 static int collect(papr_engine *e, int graph, papr_result *out, bool counts_valid)
 {
     const DevOut *h = &e->h_out->o;
     papr_result_finish(out, graph);
-    int redo = 0;
+    int redo = 0; // bit 0: the device's levels are not the host's; bit 1: the counts are invalid / a window was missed
     if (out->nlevels > 0) {
         bool same = h->lv.L == out->nlevels &&
                     memcmp(h->lv.level, out->level, sizeof(float) * (size_t)out->nlevels) == 0;
-        if (!same || !counts_valid || (h->counts[PAPR_MAX_LEVELS] != 0)) redo = 1;
+        if (!same) redo |= 1;
+        if (!counts_valid || (h->counts[PAPR_MAX_LEVELS] != 0)) redo |= 2;
         if (!redo)
             for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)h->counts[j];
     }
@@ -787,6 +807,22 @@ static int run_exact_ccdf(papr_engine *e, const float *d_iq, u64 n, const float 
         else level_count[j] = (int64_t)h->counts[j];
     }
     return PAPR_OK;
+}
+
+// The fused sweep's cells and fine table are still on the device: count again against out->level[] (the
+// levels of the exact sum).  0 = out->level_count filled; 1 = a level falls outside its window (the caller
+// runs the exact pass); < 0 = error.
+static int recount(papr_engine *e, papr_result *out)
+{
+    int rc = upload_levels(e, out->level, out->nlevels, out->stats.peak);
+    if (rc) return rc;
+    if ((rc = enqueue_resolve(e))) return rc;
+    if ((rc = enqueue_fetch(e))) return rc;
+    CU(cudaStreamSynchronize(e->stream));
+    const DevOut *h = &e->h_out->o;
+    if (h->counts[PAPR_MAX_LEVELS] != 0) return 1;
+    for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)h->counts[j];
+    return 0;
 }
 
 static void finish_timing(papr_engine *e, papr_result *out)
@@ -1042,13 +1078,12 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
         e->launches += 3;
         if (chained) {
             if ((rc = enqueue_scan_tma(e, d_iq, n, 0, true))) return rc;
-            if ((rc = enqueue_xt_chain(e, d_iq, n))) return rc;
-            if ((rc = enqueue_finalize_levels(e, n, graph, true))) return rc;
+            if ((rc = enqueue_xt_epilogue(e, d_iq, n, graph))) return rc; // chain || finalize + levels + counts
         } else {
             if ((rc = enqueue_scan(e, true, true, d_iq, n, 0, true))) return rc;
             if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
+            if ((rc = enqueue_resolve(e))) return rc;
         }
-        if ((rc = enqueue_resolve(e))) return rc;
     } else {
         if ((rc = enqueue_scan(e, true, false, d_iq, n, 0, true))) return rc;
         if ((rc = enqueue_finalize_levels_exact(e, d_iq, n, graph, exact))) return rc;
@@ -1061,6 +1096,7 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if (chained) {
         e->xt_status = e->h_out->o.chain[0];
         e->xt_why = e->h_out->o.chain[1];
+        if (e->xt_status == XT_OK) out->stats.sum = e->h_out->o.chain_exact; // replaces the fixed-order sum of the CTA partials
         if (e->xt_status == XT_FALLBACK) { // the device chain could not vouch for its sum: the two-sweep emulation
             double s = 0.0;
             if ((rc = exact_sequential_sum(e, d_iq, n, &s)) < 0) return rc;
@@ -1070,10 +1106,21 @@ extern "C" int papr_analyze_device(papr_engine *e, const float *d_iq, uint64_t n
     if (chained) out->sum_path = e->xt_status == XT_OK ? 1u : e->xt_status == XT_FALLBACK ? (2u | ((unsigned)e->xt_why << 8)) : 0u;
     else out->sum_path = exact && std::isfinite(out->stats.sum) ? 2u : 0u;
     if ((rc = fix_nan_sign(e, d_iq, n, 0, &out->stats))) return rc;
-    if (collect(e, graph, out, true)) {
-        out->fused_miss = mode == PAPR_MODE_FUSED;
-        rc = run_exact_ccdf(e, d_iq, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
-        if (rc) return rc;
+    if (const int redo = collect(e, graph, out, true)) {
+        // chained: the counts were taken against levels derived from the fixed-order sum.  If those differ from
+        // the levels of the exact sum (rare), the cells and the fine table still hold everything needed.
+        bool recounted = false;
+        if (chained && (redo & 1)) {
+            if ((rc = recount(e, out)) < 0) return rc;
+            recounted = rc == 0;
+        }
+        if (recounted) {
+            out->fused_miss = 2;
+        } else {
+            out->fused_miss = mode == PAPR_MODE_FUSED;
+            rc = run_exact_ccdf(e, d_iq, n, out->level, out->nlevels, out->stats.peak, out->level_count, false);
+            if (rc) return rc;
+        }
         CU(cudaEventRecord(e->ev_end, e->stream));
         CU(cudaStreamSynchronize(e->stream));
     }
@@ -1258,7 +1305,7 @@ extern "C" int papr_shard_finish(papr_engine *e, int graph, papr_result *out)
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     stats_to_host(e->h_out->o.merged, &out->stats);
-    int redo = collect(e, graph, out, true);
+    int redo = collect(e, graph, out, true) ? 1 : 0;
     finish_timing(e, out);
     out->mode_used = e->shard_mode;
     out->fused_miss = redo;
@@ -1367,20 +1414,20 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
                                (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
         papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
                                       &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
-                                      ++e->xseq[XK_STATS], e->stream, e->d_xt_parts);
-        papr_launch_xt_chain_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
-                               d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], e->stream);
-        papr_launch_levels(e->d_xt_parts, e->peers.world, e->tables(graph), graph, &e->d_out->merged, &e->d_out->lv,
-                           &e->d_out->counts[PAPR_MAX_LEVELS], e->stream, e->d_xt_chain, e->d_out->chain);
-        e->launches += 4;
+                                      ++e->xseq[XK_STATS], e->stream, e->d_xt_parts, e->epilogue_bias);
+        // the chain (with its exchange) side by side with this shard's counts against the levels of the fixed-order sums
+        papr_launch_xt_epilogue_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
+                                  d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], epilogue_args(e, n, graph),
+                                  e->num_sms, e->stream);
+        e->launches += 3;
     } else {
         if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
         papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
                                       &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
                                       ++e->xseq[XK_STATS], e->stream);
         e->launches += 1;
+        if ((rc = enqueue_resolve(e))) return rc;
     }
-    if ((rc = enqueue_resolve(e))) return rc;
     papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
     e->launches += 1;
     if ((rc = enqueue_fetch(e))) return rc;
@@ -1391,11 +1438,31 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     if (chained) { // identical on every rank: all of them walked the same lists
         e->xt_status = e->h_out->o.chain[0];
         e->xt_why = e->h_out->o.chain[1];
+        if (e->xt_status == XT_OK) out->stats.sum = e->h_out->o.chain_exact; // replaces the merged fixed-order sums
         out->sum_path = e->xt_status == XT_OK ? 1u : e->xt_status == XT_FALLBACK ? (2u | ((unsigned)e->xt_why << 8)) : 0u;
     }
-    // merged stats and the summed status word are identical on every rank, so every rank takes the
-    // same branch here: thresholds outside the predicted windows somewhere -> exact pass everywhere
-    if (collect(e, graph, out, true)) {
+    // merged stats, the chained sum and the summed status word are identical on every rank, so every rank takes
+    // the same branches here
+    int redo = collect(e, graph, out, true);
+    if (chained && (redo & 1)) {
+        // only the levels moved (they were derived from the fixed-order sums while the chain was running): every
+        // rank counts again against the levels of the chained sum - the cells and fine tables are still in place
+        if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
+        if ((rc = enqueue_resolve(e))) return rc;
+        papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
+        e->launches += 1;
+        if ((rc = enqueue_fetch(e))) return rc;
+        CU(cudaEventRecord(e->ev_end, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+        if (e->h_out->o.plan.pad) return fail(e, PAPR_ERR_INTERNAL, "peer exchange timed out (a rank did not take part)");
+        redo = e->h_out->o.counts[PAPR_MAX_LEVELS] != 0 ? 2 : 0;
+        if (!redo) {
+            out->fused_miss = 2;
+            for (int j = 0; j < out->nlevels; ++j) out->level_count[j] = (int64_t)e->h_out->o.counts[j];
+        }
+    }
+    // thresholds outside the predicted windows somewhere -> exact pass everywhere
+    if (redo) {
         out->fused_miss = 1;
         if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;
         CU(cudaMemsetAsync(e->d_work, 0, offsetof(DevWork, wp), e->stream)); // histogram scratch only

@@ -11,9 +11,11 @@
 //                          exactly as the reference's adds do; two ballots carry the parity from lane to
 //                          lane; per-lane totals are folded once per tile.
 //   papr_xt_compose_kernel 32 tile runs -> one super-tile run (ordered, associative composition)
-//   papr_xt_chain_kernel   one CTA: approximate prefix sums locate every binade crossing of the running
-//                          sum down to 8 samples; the stretches between crossings are composed in
-//                          parallel; what remains is a list of < 100 items applied in order.
+//   the chain              one CTA (CTA 0 of papr_xt_epilogue_kernel; papr_xt_chain_x_kernel when sharded):
+//                          approximate prefix sums locate every binade crossing of the running sum down to
+//                          one sample; the stretches between crossings are composed in parallel; what
+//                          remains is a list of < 100 items applied in order.
+//   papr_xt_epilogue_kernel (single shard) the chain side by side with finalize + levels + level counts
 // Everything is verified while it is applied (state inside the assumed binade before and after each run);
 // a failed check only ever sends the analysis to the slower two-sweep emulation, never to a wrong sum.
 #include <cuda.h>
@@ -184,9 +186,9 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
         unsigned *s_fb = s_hist + (XT_NCELLS + 2);
         st.g_fine = a.g_fine;
         asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
-                     : "=r"(st.smem_slot1) : "l"(s_hist + 1));
-        st.sh = pl.sh;
-        st.cell_base = do_hist ? pl.cell_base : 0x7fffffff; // no valid plan: every sample lands in slot 0
+                     : "=r"(st.smem_slot0) : "l"(s_hist));
+        st.sh = pl.sh; // (always PAPR_SH_MIN here: this sweep only follows papr_plan_pred*, the shift is compiled in)
+        st.neg_base1 = 1 - (do_hist ? pl.cell_base : 0x7fffffff); // no valid plan: every sample lands in slot 0
         st.ncells = do_hist ? min(pl.ncells, XT_NCELLS) : 0;
         st.fmask = (1u << pl.sh) - 1u;
         for (int i = threadIdx.x; i < st.ncells + 2; i += XT_THREADS) {
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(XT_THREADS, 1) papr_scan_tma_kernel(const __gr
 
             // ---- CCDF cells (papr.c:147-151)
 #pragma unroll
-            for (int u = 0; u < XT_RUN / 2; ++u) hist_pair<true, true, 4 * (XT_NCELLS + 2)>(st, v[2 * u], v[2 * u + 1]);
+            for (int u = 0; u < XT_RUN / 2; ++u) hist_pair<true, true, 4 * (XT_NCELLS + 2), PAPR_SH_MIN>(st, v[2 * u], v[2 * u + 1]);
 
             // ---- papr.c:104
             if (nc == 1) {
@@ -475,9 +477,10 @@ __device__ __forceinline__ PaprTileRun xt_pick(const PaprSuperRec &r, int k) // 
 
 __global__ void __launch_bounds__(1024) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
                                                                unsigned ntiles, const PaprTileRun *multi_tile,
-                                                               PaprSuperRec *super, PaprSuperRec *hyper)
+                                                               PaprSuperRec *super, PaprSuperRec *hyper, u64 *zero_word)
 {
     __shared__ PaprSuperRec s_rec[32];
+    if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0; // the status word of the counts that follow (RES_* bits are OR-ed in)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
     const unsigned nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
@@ -545,9 +548,9 @@ __global__ void __launch_bounds__(1024) papr_xt_compose_kernel(const PaprTileRun
 }
 
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi_tile,
-                            PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s)
+                            PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s, unsigned long long *zero_word)
 {
-    papr_xt_compose_kernel<<<grid, 1024, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super, hyper);
+    papr_xt_compose_kernel<<<grid, 1024, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super, hyper, zero_word);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1079,46 +1082,175 @@ __device__ int xt_chain_prepare(const XtCtx &c, double pre_approx, PaprChainList
     return s_status;
 }
 
-// single shard: prepare + walk
-__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_kernel(XtCtx c, PaprChainList *out)
+// papr.c:147-151 restated (as in papr_count_kernel), by all XT_CHAIN_T threads of a CTA: levels j0, j0 + stride, ...
+// below L: counts[j] = samples above the cell range + samples in the cells above cell(T_j) + the fine counters of
+// the values of that cell that are > T_j.  A threshold outside the planned cells / windows => RES_MISS.
+template <class LevelOf>
+static __device__ void xt_count_levels(const PaprEpilogueArgs &a, int L, int j0, int stride, LevelOf level_of)
 {
-    __shared__ XtShared sh;
-    const int st = xt_chain_prepare(c, 0.0, out, &sh);
-    if (threadIdx.x == 0 && st == XT_OK) {
-        double s = 0.0;
-        int why = XW_NONE;
-#ifdef XT_TIMING
-        unsigned long long w0, w1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
-#endif
-        out->status = xt_walk(sh.item, sh.n, &s, &why);
-#ifdef XT_TIMING
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
-        printf("xt walk ns: %llu\n", w1 - w0);
-#endif
-        out->why = why;
-        out->exact = s;
+    __shared__ u64 s_red[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const PaprPlan pl = *a.plan;
+    if (pl.status & PLAN_BSEARCH) return;
+    const unsigned fmask = (1u << pl.sh) - 1u;
+    for (int j = j0; j < L; j += stride) {
+        const unsigned tbits = __float_as_uint(level_of(j));
+        const int d = (int)(tbits >> pl.sh) - pl.cell_base;
+        const bool in = (pl.status & PLAN_HIST) && (unsigned)d < (unsigned)pl.ncells;
+        const unsigned fb = in ? a.fine_base[d] : 0;
+        if (!fb) {
+            if (t == 0) { atomicOr(a.status_word, (u64)RES_MISS); a.counts[j] = 0; }
+            continue;
+        }
+        const u64 *f = a.g_fine + (fb - 1u);
+        u64 acc = 0;
+        for (unsigned k = (tbits & fmask) + 1 + t; k <= fmask; k += XT_CHAIN_T) acc += f[k];
+        for (int cc = d + 1 + t; cc < pl.ncells; cc += XT_CHAIN_T) acc += a.g_hist[cc];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            acc = s_red[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+            if (lane == 0) a.counts[j] = acc + *a.g_over;
+        }
+        __syncthreads();
     }
 }
 
-void papr_launch_xt_chain(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code, const PaprTileRun *multi,
-                          const PaprTileRun *multi_tile, unsigned ntiles, const float *iq, unsigned long long nsamples,
-                          PaprChainList *out, cudaStream_t s)
+// ------------------------------------------------------------------------------------------------
+// single shard: the chain SIDE BY SIDE with the scalar epilogue and the level counts (one launch instead of
+// chain -> finalize+levels -> count).  CTA 0 chains the sequential sum.  Every other CTA folds the CTA partials
+// itself (148 x 72 B), evaluates papr.c:131-141 with the FIXED-ORDER sum of the partials - which differs from
+// the sequential sum by ~1e-12 relative, almost never enough to move a float32 level - and counts its share of
+// the levels; CTA 1 also stores the statistics and the level table.  The host then derives the levels from the
+// chain's exact sum with its own libm, as it always does, and accepts the counts only if the device's levels are
+// bit-identical to those; otherwise (about once in 10^4 analyses) the counts are taken again with the right
+// levels (papr_engine.cu: recount).  `bias` scales the sum the speculative levels are derived from (test hook).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_kernel(XtCtx c, PaprChainList *out, const PaprEpilogueArgs a)
+{
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (blockIdx.x == 0) {
+        __shared__ XtShared sh;
+        const int st = xt_chain_prepare(c, 0.0, out, &sh);
+        if (t == 0) {
+            int status = st, why = out->why;
+            double s = 0.0;
+            if (st == XT_OK) {
+                why = XW_NONE;
+                status = xt_walk(sh.item, sh.n, &s, &why);
+                out->status = status; out->why = why; out->exact = s;
+            }
+            a.chain_report[0] = status;
+            a.chain_report[1] = why;
+            *a.chain_exact = s;
+        }
+        return;
+    }
+    __shared__ double s_sum[32];
+    __shared__ int s_val[PAPR_NTRACK][32];
+    __shared__ u64 s_idx[PAPR_NTRACK][32];
+    __shared__ double s_avg, s_ratio;
+    // ---- fold the CTA partials: fixed order, (value desc, index asc) = first occurrence (papr.c:105-126)
+    double sum = 0.0;
+    int val[PAPR_NTRACK];
+    u64 idx[PAPR_NTRACK];
+#pragma unroll
+    for (int k = 0; k < PAPR_NTRACK; ++k) { val[k] = 0; idx[k] = 0; }
+    for (int i = t; i < a.nctas; i += XT_CHAIN_T) {
+        sum += a.wp[i].sum;
+#pragma unroll
+        for (int k = 0; k < PAPR_NTRACK; ++k) {
+            const int v = a.wp[i].val[k];
+            const u64 ix = a.wp[i].idx[k];
+            if (v > 0 && better(v, ix, val[k], idx[k])) { val[k] = v; idx[k] = ix; }
+        }
+    }
+    for (int round = 0; round < 2; ++round) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_down_sync(FULL, sum, o);
+#pragma unroll
+            for (int k = 0; k < PAPR_NTRACK; ++k) {
+                const int v = __shfl_down_sync(FULL, val[k], o);
+                const u64 ix = __shfl_down_sync(FULL, idx[k], o);
+                if (v > 0 && better(v, ix, val[k], idx[k])) { val[k] = v; idx[k] = ix; }
+            }
+        }
+        if (round == 0) {
+            if (lane == 0) {
+                s_sum[warp] = sum;
+#pragma unroll
+                for (int k = 0; k < PAPR_NTRACK; ++k) { s_val[k][warp] = val[k]; s_idx[k][warp] = idx[k]; }
+            }
+            __syncthreads();
+            sum = s_sum[lane]; // (every warp folds the 32 warp results again: identical everywhere)
+#pragma unroll
+            for (int k = 0; k < PAPR_NTRACK; ++k) { val[k] = s_val[k][lane]; idx[k] = s_idx[k][lane]; }
+        }
+    }
+    if (t == 0) {
+        PaprDevStats m;
+        m.sum = sum;
+        m.n = a.n;
+#pragma unroll
+        for (int k = 0; k < PAPR_NTRACK; ++k) { m.val[k] = val[k]; m.idx[k] = idx[k]; }
+        m.flags = isfinite(sum) ? 0u : PAPR_FLAG_NONFINITE;
+        const double avg = __ddiv_rn(__dmul_rn(sum, a.bias), (double)(long long)a.n);
+        s_avg = avg;
+        s_ratio = __ddiv_rn((double)__int_as_float(val[TR_PEAK]), avg);
+        if (blockIdx.x == 1) {
+            *a.local = m;
+            *a.merged = m;
+            a.lv->avg = avg;
+            a.lv->ratio = s_ratio;
+            a.lv->graph = a.graph;
+        }
+    }
+    __syncthreads();
+    const double avg = s_avg, ratio = s_ratio;
+    int L = 0; // number of j with ratio >= ratio_min[j] (non-decreasing table; a NaN ratio reaches no level)
+    for (int j0 = 0; j0 < a.tb.nlevels_max; j0 += XT_CHAIN_T)
+        L += __syncthreads_count(j0 + t < a.tb.nlevels_max && ratio >= a.tb.ratio_min[j0 + t]);
+    if (blockIdx.x == 1) {
+        if (t == 0) a.lv->L = L;
+        for (int j = t; j < L; j += XT_CHAIN_T) a.lv->level[j] = __double2float_rn(__dmul_rn(a.tb.pow10[j], avg));
+    }
+    // ---- this CTA's levels
+    xt_count_levels(a, L, (int)blockIdx.x - 1, (int)gridDim.x - 1,
+                    [&](int j) { return __double2float_rn(__dmul_rn(a.tb.pow10[j], avg)); });
+}
+
+void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code,
+                             const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles, const float *iq,
+                             unsigned long long nsamples, PaprChainList *out, const PaprEpilogueArgs &a, int grid, cudaStream_t s)
 {
     XtCtx c;
     c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
     c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
     c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
-    papr_xt_chain_kernel<<<1, XT_CHAIN_T, 0, s>>>(c, out);
+    papr_xt_epilogue_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, a);
 }
 
 // sharded (one process per GPU): every rank builds the list of its own shard - placing it after the lower
 // ranks' approximate sums, which the statistics exchange of this analysis has just delivered - publishes it to
 // every peer's window over NVLink, collects the others', and walks ALL lists in rank order from a running sum
 // of 0: the same work and the same verdict on every rank, no hand-over from GPU to GPU.
-__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_x_kernel(XtCtx c, PaprChainList *out, PaprPlan *plan,
-                                                                    PaprPeers pp, u64 seq)
+// With the level counts side by side, as in the single-shard epilogue: CTA 0 is the chain; the other CTAs count
+// this shard's samples above the levels that papr_finalize_levels_x_kernel has just derived from the merged
+// FIXED-ORDER sums (a.lv) - the host verifies those levels against the ones of the chained sum afterwards.
+__global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c, PaprChainList *out, PaprPlan *plan,
+                                                                       PaprPeers pp, u64 seq, const PaprEpilogueArgs a)
 {
+    if (blockIdx.x != 0) {
+        const PaprDevLevels *lv = a.lv;
+        xt_count_levels(a, min(max(lv->L, 0), PAPR_MAX_LEVELS), (int)blockIdx.x - 1, (int)gridDim.x - 1,
+                        [&](int j) { return lv->level[j]; });
+        return;
+    }
     __shared__ XtShared sh;
     __shared__ int s_st, s_why;
     __shared__ double s_state;
@@ -1157,17 +1289,22 @@ __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_chain_x_kernel(XtCtx c, Pa
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out->status = s_st; out->why = s_why; out->exact = s_state; }
+    if (threadIdx.x == 0) {
+        out->status = s_st; out->why = s_why; out->exact = s_state;
+        a.chain_report[0] = s_st;
+        a.chain_report[1] = s_why;
+        *a.chain_exact = s_state;
+    }
 }
 
-void papr_launch_xt_chain_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
-                            const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
-                            const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
-                            unsigned long long seq, cudaStream_t s)
+void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
+                               const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
+                               const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
+                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s)
 {
     XtCtx c;
     c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
     c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
     c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
-    papr_xt_chain_x_kernel<<<1, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq);
+    papr_xt_epilogue_x_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq, a);
 }

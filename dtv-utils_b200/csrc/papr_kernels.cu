@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(PAPR_THREADS, PAPR_CTAS_PER_SM) papr_scan_kern
         st.g_fine = a.g_fine;
         // opaque to the optimiser on purpose: otherwise the window base is rematerialised per sample
         asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}"
-                     : "=r"(st.smem_slot1) : "l"(s_hist + 1));
+                     : "=r"(st.smem_slot0) : "l"(s_hist));
         st.sh = pl.sh;
         // without a valid plan (fused mode, nothing to predict from) every sample lands in slot 0
-        st.cell_base = do_hist ? pl.cell_base : 0x7fffffff;
+        st.neg_base1 = 1 - (do_hist ? pl.cell_base : 0x7fffffff);
         st.ncells = do_hist ? pl.ncells : 0;
         st.fmask = (1u << pl.sh) - 1u;
         for (int i = threadIdx.x; i < st.ncells + 2; i += PAPR_THREADS) {
@@ -211,7 +211,7 @@ __device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, Papr
 __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
                                  PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
                                  size_t stride_bytes = sizeof(PaprDevStats), const PaprChainList *chain = nullptr,
-                                 int *chain_report = nullptr)
+                                 int *chain_report = nullptr, double bias = 1.0 /* test hook: scales the sum the levels come from */)
 {
     __shared__ int s_L;
     __shared__ double s_avg;
@@ -233,7 +233,7 @@ __device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const Pa
             chain_report[1] = chain->why;
         }
         *merged = m;
-        double avg = __ddiv_rn(m.sum, (double)(long long)m.n);
+        double avg = __ddiv_rn(__dmul_rn(m.sum, bias), (double)(long long)m.n);
         double ratio = __ddiv_rn((double)__int_as_float(m.val[TR_PEAK]), avg);
         int lo = 0, hi = tb.nlevels_max; // number of j with ratio >= ratio_min[j] (non-decreasing table)
         while (lo < hi) {
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const Pap
                                                                       PaprDevStats *local, PaprTables tb, int graph,
                                                                       PaprDevStats *merged, PaprDevLevels *lv,
                                                                       u64 *status_word, PaprPlan *plan, PaprPeers pp,
-                                                                      u64 seq, PaprDevStats *parts_out)
+                                                                      u64 seq, PaprDevStats *parts_out, double bias)
 {
     reduce_partials(wp, nctas, n, local);
     __threadfence();
@@ -705,20 +705,19 @@ __global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const Pap
         reinterpret_cast<u64 *>(&s_parts[q])[w] = ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats) + w);
     }
     __syncthreads();
-    if (parts_out) { // the chain kernel comes first (it needs every shard's approximate sum); levels after it
+    if (parts_out) // the chain that follows needs every shard's approximate sum
         for (int i = threadIdx.x; i < pp.world * (int)(sizeof(PaprDevStats) / 8); i += blockDim.x)
             reinterpret_cast<u64 *>(parts_out)[i] = reinterpret_cast<const u64 *>(s_parts)[i];
-        return;
-    }
-    merge_and_levels(s_parts, pp.world, tb, graph, merged, lv, status_word);
+    // (chained: these levels come from the fixed-order sums; the host checks them against the chained sum's)
+    merge_and_levels(s_parts, pp.world, tb, graph, merged, lv, status_word, sizeof(PaprDevStats), nullptr, nullptr, bias);
 }
 
 void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
                                    PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
-                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s, PaprDevStats *parts_out)
+                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s, PaprDevStats *parts_out, double bias)
 {
     papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq,
-                                                      parts_out);
+                                                      parts_out, bias);
 }
 
 // sharded: publish this shard's level counts (+ status word), collect every rank's, add them up.

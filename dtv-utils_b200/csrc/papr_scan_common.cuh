@@ -27,9 +27,17 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p)
 
 // papr.c:103 — (I*I)+(Q*Q) with each operation rounded to float32 (the canonical x86-64 build of
 // the reference emits mulss, mulss, addss; an FMA here changes the printed percentages)
+// The two squares come from ONE packed instruction (Blackwell FMUL2, `mul.rn.f32x2`): each half is an IEEE
+// round-to-nearest-even product with denormals kept, exactly what two FMULs give; the I/Q pair already sits in
+// an aligned register pair after a 16-byte load, so nothing is moved.
 __device__ __forceinline__ float power_of(float i, float q)
 {
-    return __fadd_rn(__fmul_rn(i, i), __fmul_rn(q, q));
+    unsigned long long p, r;
+    float ii, qq;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(i), "f"(q));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(p));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ii), "=f"(qq) : "l"(r));
+    return __fadd_rn(ii, qq);
 }
 
 template <int T>
@@ -72,8 +80,8 @@ struct ScanState {
     unsigned upd;
     // pass 2
     u64 *g_fine;
-    unsigned smem_slot1; // shared-window byte address of slot 1 (= cell 0)
-    int sh, cell_base, ncells;
+    unsigned smem_slot0; // shared-window byte address of slot 0 (cell c is slot c + 1)
+    int sh, neg_base1, ncells; // neg_base1 = 1 - cell_base: slot = clamp((bits >> sh) + neg_base1, 0, ncells + 1)
     unsigned fmask;
 };
 
@@ -82,17 +90,19 @@ struct ScanState {
 // range (63 % of a Gaussian-like capture) and slot ncells+1 everything above it; every lane issues the
 // shared-memory increment (ATOMS.POPC.INC merges lanes that hit the same word, so the crowded slot 0
 // costs one update per warp) and reads the slot's fine-table base (0 = no threshold can lie here).
-template <bool STATS, bool HIST>
+// SH > 0: the shift is a compile-time constant (the fused plans always use PAPR_SH_MIN), which lets shift and
+// subtraction fuse into one LEA.HI; the two-sided clamp is one DPX instruction (VIMNMX.RELU).
+template <bool STATS, bool HIST, int SH = 0>
 __device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, unsigned bits)
 {
     // shared-window byte address of the sample's slot
-    int d = (int)(bits >> st.sh) - st.cell_base;
+    int c = (int)(bits >> (SH > 0 ? SH : st.sh));
     // a NaN power exceeds no level (`value > level[j]` is false, papr.c:148); only the stand-alone CCDF
     // pass can meet one with levels to count against - with the statistics in the same sweep the sum is
     // NaN too and the reference prints no levels at all
-    if (!STATS) d = bits > 0x7f800000u ? -1 : d;
-    d = max(min(d, st.ncells), -1);
-    return st.smem_slot1 + ((unsigned)d << 2);
+    if (!STATS) c = bits > 0x7f800000u ? 0 : c;
+    const int slot = __viaddmin_s32_relu(c, st.neg_base1, st.ncells + 1); // max(min(c + neg_base1, ncells + 1), 0)
+    return st.smem_slot0 + ((unsigned)slot << 2);
 }
 
 // FB_OFF: byte distance from a cell's counter to its fine-table base (the second array of the shared window)
@@ -113,12 +123,12 @@ __device__ __forceinline__ void fine_bump(unsigned long long *g_fine, unsigned f
 }
 
 // the two samples of one 16-byte load
-template <bool STATS, bool HIST, int FB_OFF = 4 * (PAPR_NCELLS_MAX + 2)>
+template <bool STATS, bool HIST, int FB_OFF = 4 * (PAPR_NCELLS_MAX + 2), int SH = 0>
 __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, float v1)
 {
     const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
-    const unsigned f0 = hist_bump<FB_OFF>(hist_slot(st, b0));
-    const unsigned f1 = hist_bump<FB_OFF>(hist_slot(st, b1));
+    const unsigned f0 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b0));
+    const unsigned f1 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b1));
     if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
         fine_bump(st.g_fine, f0, b0, st.fmask);
         fine_bump(st.g_fine, f1, b1, st.fmask);

@@ -72,7 +72,7 @@ typedef struct papr_result {
     int64_t  level_count[PAPR_MAX_LEVELS]; /* samples with power > level[j] papr.c:147-151,179-183 */
     /* diagnostics (not printed) */
     int32_t  mode_used;                    /* PAPR_MODE_TWO_PASS or PAPR_MODE_FUSED */
-    int32_t  fused_miss;                   /* 1 if the fused pass missed and the exact pass re-ran */
+    int32_t  fused_miss;                   /* 1 if the fused pass missed and the exact pass re-ran; 2 if only the level counts were taken again */
     float    device_ms;                    /* GPU time of the analysis (CUDA events on the engine stream) */
     float    scan_ms;                      /* GPU time of the dominant scan kernel launch(es) */
     uint32_t kernel_launches;              /* kernels launched for this analysis */

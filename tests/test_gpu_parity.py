@@ -204,6 +204,34 @@ def test_fused_stage_api_and_forced_miss(built, eng, torch_cuda):
     assert miss2
 
 
+def test_epilogue_levels_are_verified_and_recounted(built, eng, torch_cuda):
+    """Single shard, sequential sum chained on the device: the epilogue derives avg / L / levels from the
+    fixed-order sum of the CTA partials while the chain is still running (papr_xt_epilogue_kernel).  The host
+    accepts its counts only if those levels are bit-identical to the levels of the exact sum; a (forced)
+    disagreement must be caught and the counts taken again from the cells + fine table still on the device."""
+    n = (1 << 24) + 4096 * 3 + 17
+    f = fixtures.siggen(0, n, 5)
+    d = _dev(torch_cuda, f)
+    eng.set("mode", 2)
+    try:
+        for graph in (False, True):
+            want = oracle_binding.run_image(f.tobytes(), graph)
+            r0 = eng.analyze_device(d, n, graph)
+            assert r0.fused_miss == 0 and (r0.sum_path & 0xff) == 1 and built.format_result(r0) == want
+            # 3e-7: a few float32 levels move by one ulp, all stay inside their windows; 1.25: every level leaves its
+            # window (the speculative counts report a miss as well) - both are settled by one more tiny kernel
+            for bias in (1.0 + 3e-7, 1.25, 0.5):
+                eng.set("epilogue_bias", bias)
+                r = eng.analyze_device(d, n, graph)
+                assert r.fused_miss == 2, (graph, bias, r.fused_miss)
+                assert r.stats.as_tuple() == r0.stats.as_tuple() and r.counts() == r0.counts()
+                assert built.format_result(r) == want
+            eng.set("epilogue_bias", 1.0)
+    finally:
+        eng.set("epilogue_bias", 1.0)
+        eng.set("mode", 0)
+
+
 def test_generic_bsearch_kernel(built, eng, torch_cuda):
     """Force the fallback for plans whose fine table does not fit (PLAN_BSEARCH)."""
     eng.set("fine_bytes_log2", 8)
@@ -289,6 +317,15 @@ def test_config1_4gib_cli_vs_reference_binary(built, eng, torch_cuda, tmp_path_f
         if os.environ.get("PAPR_B200_TEST_GRAPH_4GIB"):  # ~2 min of CPU for the reference
             want_g = subprocess.run([ref, "-g", path], capture_output=True).stdout
             assert subprocess.run([built.cli_path(), "-g", path], capture_output=True).stdout == want_g
+        else:  # by default -g on the first 512 MiB of the same capture (2^26 samples, ~9 s of CPU for the reference)
+            m = 1 << 26
+            os.truncate(path, 8 * m)
+            want_g = subprocess.run([ref, "-g", path], capture_output=True).stdout
+            assert subprocess.run([built.cli_path(), "-g", path], capture_output=True).stdout == want_g
+            for mode in (1, 2):
+                eng.set("mode", mode)
+                assert built.format_result(eng.analyze_device(d, m, True)) == want_g
+            eng.set("mode", 0)
     finally:
         if os.path.exists(path):
             os.unlink(path)

@@ -95,6 +95,15 @@ for graph in (False, True):
     res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)
     eng.set("predict_bias", 1.0)
     ok &= res.fused_miss == 1 and pb.format_result(res) == want
+    # the counts are taken against levels derived from the fixed-order sums while the chain is still running; a
+    # (forced) disagreement with the levels of the chained sum must make every rank count again, together
+    for bias in (1.0 + 3e-7, 1.25):
+        eng.set("epilogue_bias", bias)
+        res = pb.analyze_sharded(eng, d, n, rank * n, graph, mode=2)
+        eng.set("epilogue_bias", 1.0)
+        ok &= res.fused_miss == 2 and pb.format_result(res) == want
+        ok &= struct.pack("<d", res.stats.sum) == struct.pack("<d", seq_sum)
+        if not ok: print("rank", rank, "graph", graph, "bias", bias, "fused_miss", res.fused_miss, flush=True)
     pinned = d.cpu().pin_memory()
     res = pb.analyze_sharded(eng, None, n, rank * n, graph, host_image=pinned)
     ok &= pb.format_result(res) == want

@@ -16,10 +16,10 @@ for _ in range(3):
     r = eng.analyze_device(d, n, g)
 print(r.device_ms, r.scan_ms, r.sum_path)
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"papr_" -s 8 -c 8 --csv --log-file gpurun_out/r02_quick_${1:-1dB}.csv python /tmp/xt_one.py ${1:+g} > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__issue_active.avg.pct_of_peak_sustained_elapsed,dram__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"papr_" -s 7 -c 7 --csv --log-file gpurun_out/r02b_quick_${1:-1dB}.csv python /tmp/xt_one.py ${1:+g} > /dev/null 2>&1
 python - <<PY
 import csv
-rows=[r for r in csv.reader(open("gpurun_out/r02_quick_${1:-1dB}.csv")) if len(r)>10]
+rows=[r for r in csv.reader(open("gpurun_out/r02b_quick_${1:-1dB}.csv")) if len(r)>10]
 h=rows[0]
 for r in rows[1:]:
     print(r[h.index("Kernel Name")][:40], r[h.index("Metric Name")], r[h.index("Metric Value")])
