@@ -272,7 +272,8 @@ struct PaprEpilogueArgs {
 void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
                                const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
                                const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
-                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s);
+                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s,
+                               int decline /* this rank has no runs: publish an empty list marked XT_FALLBACK */);
 void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code,
                              const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles, const float *iq,
                              unsigned long long nsamples, PaprChainList *out, const PaprEpilogueArgs &a, int grid, cudaStream_t s);

@@ -228,8 +228,9 @@ struct papr_engine {
     int grid_per_sm = 1;
     u64 fused_min_samples = 1ull << 24;
     int fine_bytes_log2 = 26; // 64 MiB fine table
-    int p2p_chain = -1;       // sharded in-kernel path: -1 = chain the sequential sum on the device if THIS shard qualifies;
-                              // 0 / 1 = what the ranks agreed on (all must take the same path: papr.py settles it)
+    int p2p_chain = -1;       // sharded in-kernel path: -1 = chain the sequential sum on the device if this shard qualifies
+                              // (a rank whose shard does not declines inside the exchange: every rank then reports the
+                              // fall-back); 0 = this rank always declines; 1 = fail if this shard does not qualify
     int o_direct = 0;         // 1: regular files are also opened with O_DIRECT (NVMe -> pinned staging, no page cache)
     int exact_sum = -1;       // != 0 (default): the reference's sequential double sum, bit for bit, on every path; 0: off
     // exact sequential-sum scratch (grown on demand)
@@ -1394,9 +1395,10 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     int rc;
     CU(cudaEventRecord(e->ev_begin, e->stream));
     if ((rc = enqueue_reset(e))) return rc;
-    // the sequential sum inside the sweep: all ranks must agree on taking this path (same n is not required, the
-    // tunable and the minimum size are): every rank then runs the chain exchange
-    const bool chained = e->p2p_chain < 0 ? xt_applicable(e, n) : (e->p2p_chain != 0 && xt_applicable(e, n));
+    // the sequential sum inside the sweep, if this shard qualifies (tunable p2p_chain = 0: never).  A rank that does not
+    // still takes part in the chain exchange - it declines there, and then every rank reports the fall-back - so the
+    // sequence of exchanges never depends on the shard sizes and the ranks need not agree on anything beforehand.
+    const bool chained = e->p2p_chain != 0 && xt_applicable(e, n);
     if (e->p2p_chain > 0 && !chained) return fail(e, PAPR_ERR_ARG, "p2p_chain = 1 but this shard is too small for the chained sweep");
     e->xt_status = -1;
     papr_launch_presample(d_iq, std::min<u64>(n, kMaxLaunchSamples * 2 - PAPR_BATCH_SAMPLES),
@@ -1406,45 +1408,42 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
                             ++e->xseq[XK_PRE], e->stream, chained ? XT_NCELLS : PAPR_NCELLS_MAX);
     papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 3;
+    const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
     if (chained) {
         if ((rc = enqueue_scan_tma(e, d_iq, n, first, true))) return rc;
-        const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
         const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES, nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
         papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super, e->d_xt_hyper,
                                (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
-        papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                      &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
-                                      ++e->xseq[XK_STATS], e->stream, e->d_xt_parts, e->epilogue_bias);
-        // the chain (with its exchange) side by side with this shard's counts against the levels of the fixed-order sums
-        papr_launch_xt_epilogue_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
-                                  d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], epilogue_args(e, n, graph),
-                                  e->num_sms, e->stream);
-        e->launches += 3;
+        e->launches += 1;
     } else {
         if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
-        papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                      &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
-                                      ++e->xseq[XK_STATS], e->stream);
-        e->launches += 1;
-        if ((rc = enqueue_resolve(e))) return rc;
     }
+    // every rank's pass-1 state -> merged statistics and the levels of the merged FIXED-ORDER sums ...
+    papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
+                                  &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
+                                  ++e->xseq[XK_STATS], e->stream, nullptr, e->epilogue_bias);
+    // ... then the chain (with its exchange) side by side with this shard's counts against those levels
+    papr_launch_xt_epilogue_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
+                              d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], epilogue_args(e, n, graph),
+                              e->num_sms, e->stream, chained ? 0 : 1);
     papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
-    e->launches += 1;
+    e->launches += 3;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     if (e->h_out->o.plan.pad) return fail(e, PAPR_ERR_INTERNAL, "peer exchange timed out (a rank did not take part)");
     stats_to_host(e->h_out->o.merged, &out->stats);
-    if (chained) { // identical on every rank: all of them walked the same lists
+    { // identical on every rank: all of them walked the same lists (a rank that declined makes everyone fall back)
         e->xt_status = e->h_out->o.chain[0];
         e->xt_why = e->h_out->o.chain[1];
         if (e->xt_status == XT_OK) out->stats.sum = e->h_out->o.chain_exact; // replaces the merged fixed-order sums
         out->sum_path = e->xt_status == XT_OK ? 1u : e->xt_status == XT_FALLBACK ? (2u | ((unsigned)e->xt_why << 8)) : 0u;
+        if (e->exact_sum == 0) out->sum_path = 0; // any fixed order was asked for
     }
     // merged stats, the chained sum and the summed status word are identical on every rank, so every rank takes
     // the same branches here
     int redo = collect(e, graph, out, true);
-    if (chained && (redo & 1)) {
+    if (redo & 1) {
         // only the levels moved (they were derived from the fixed-order sums while the chain was running): every
         // rank counts again against the levels of the chained sum - the cells and fine tables are still in place
         if ((rc = upload_levels(e, out->level, out->nlevels, out->stats.peak))) return rc;

@@ -559,7 +559,7 @@ void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, u
 enum { // PaprChainList.why
     XW_NONE = 0, XW_TOO_MANY_CROSSINGS = 1, XW_SUPER_MISPREDICTED = 2, XW_TILE_NO_CANDIDATE = 3, XW_TWO_CROSSINGS_IN_TILE = 4,
     XW_BATCH_NOT_FOUND = 5, XW_LANE_NOT_FOUND = 6, XW_TOO_MANY_ITEMS = 7, XW_WALK_BINADE = 8, XW_WALK_OVERFLOW = 9,
-    XW_WALK_LITERAL = 10, XW_WALK_ABS = 11, XW_START_UNKNOWN = 12,
+    XW_WALK_LITERAL = 10, XW_WALK_ABS = 11, XW_START_UNKNOWN = 12, XW_DECLINED = 13,
 };
 
 struct XtCtx {
@@ -1242,8 +1242,12 @@ void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *supe
 // With the level counts side by side, as in the single-shard epilogue: CTA 0 is the chain; the other CTAs count
 // this shard's samples above the levels that papr_finalize_levels_x_kernel has just derived from the merged
 // FIXED-ORDER sums (a.lv) - the host verifies those levels against the ones of the chained sum afterwards.
+// decline != 0: this rank's sweep produced no runs (shard too small for the TMA-fed sweep, or the exact sum is switched
+// off): it publishes an empty list marked XT_FALLBACK, so that EVERY rank reports the fall-back - no agreement between
+// the ranks is needed beforehand, and the exchange sequence is the same whatever the shard sizes are.
 __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c, PaprChainList *out, PaprPlan *plan,
-                                                                       PaprPeers pp, u64 seq, const PaprEpilogueArgs a)
+                                                                       PaprPeers pp, u64 seq, const PaprEpilogueArgs a,
+                                                                       int decline)
 {
     if (blockIdx.x != 0) {
         const PaprDevLevels *lv = a.lv;
@@ -1257,7 +1261,13 @@ __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c,
     double pre = 0.0;
     for (int q = 0; q < pp.rank; ++q)
         pre += __longlong_as_double((long long)ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats.sum)));
-    xt_chain_prepare(c, pre, out, &sh);
+    if (decline) {
+        if (threadIdx.x == 0) { out->n = 0; out->status = XT_FALLBACK; out->why = XW_DECLINED; out->approx = 0.0; sh.n = 0; }
+        __threadfence();
+        __syncthreads();
+    } else {
+        xt_chain_prepare(c, pre, out, &sh);
+    }
     // header + the items in use
     const int words = (int)((offsetof(PaprChainList, item) + sizeof(PaprChainItem) * (size_t)max(out->n, 0)) / 8);
     xchg_publish(pp, XK_CHAIN, offsetof(PaprXchgSlot, chain), reinterpret_cast<const u64 *>(out), words, seq);
@@ -1300,11 +1310,11 @@ __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c,
 void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
                                const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
                                const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
-                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s)
+                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s, int decline)
 {
     XtCtx c;
     c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
     c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
     c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
-    papr_xt_epilogue_x_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq, a);
+    papr_xt_epilogue_x_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq, a, decline);
 }

@@ -129,7 +129,8 @@ __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, 
     const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
     const unsigned f0 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b0));
     const unsigned f1 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b1));
-    if (f0 | f1) { // some lane of the warp sits in a cell that may hold a threshold: count it per value
+    if (f0 | f1) { // a lane in a cell that may hold a threshold: count it per value.  (A per-lane branch on purpose: a
+                   // vote would make it warp-uniform but costs more - ptxas guards every *_sync vote with a BRA.DIV.)
         fine_bump(st.g_fine, f0, b0, st.fmask);
         fine_bump(st.g_fine, f1, b1, st.fmask);
     }

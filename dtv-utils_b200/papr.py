@@ -647,16 +647,8 @@ def _analyze_sharded_stream_ordered(engine: "Engine", d_iq, nsamples, first_inde
         if p2p is None:
             p2p = engine._p2p = attach_peer_exchange(engine, group)
         if p2p:
-            # every rank must take the same path through the exchange kernels: the sequential sum is chained on the
-            # device only if the smallest shard is large enough for the TMA-fed sweep (agreed once per shard size)
-            agreed = getattr(engine, "_chain_ok", None)
-            if agreed is None:
-                agreed = engine._chain_ok = {}
-            if nsamples not in agreed:
-                t = torch.tensor([nsamples], dtype=torch.int64, device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-                agreed[nsamples] = int(t.item()) >= 8192
-            engine.set("p2p_chain", 1 if agreed[nsamples] else 0)
+            # (no agreement needed: a rank whose shard is too small for the chained sweep declines inside the chain
+            # exchange, and then every rank reports the fall-back - sum_path 2 - together)
             try:
                 res = engine.shard_analyze_p2p(d_iq, nsamples, first_index, graph)
             except PaprError:

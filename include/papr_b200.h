@@ -101,10 +101,12 @@ void *papr_engine_stream(papr_engine *e);
  * double sum (papr.c:104) bit for bit on every path - inside the fused sweep for large device-resident shards
  * (papr_result.sum_path says which way), 0 = any fixed summation order; "o_direct": 1 = regular files are also opened with O_DIRECT and every
  * 4096-byte-aligned piece is read straight into the pinned staging slots, bypassing the page cache (silently buffered
- * where the file system refuses O_DIRECT, e.g. tmpfs); "p2p_chain": -1 (default) / 0 / 1 = whether papr_shard_analyze_p2p chains the
- * sequential sum on the device - every rank must take the same path, so a caller whose shards differ in size sets it
- * to what all ranks agreed on (shards below 8192 samples cannot; dtv_utils_b200.analyze_sharded settles it once per
- * shard size); "xchg_timeout_s": how long the in-kernel
+ * where the file system refuses O_DIRECT, e.g. tmpfs); "p2p_chain": whether papr_shard_analyze_p2p chains the
+ * sequential sum on the device: -1 (default) = if this rank's shard qualifies (>= 8192 samples); 0 = never; 1 = fail if
+ * it does not qualify.  A rank that does not chain still takes part in the chain exchange and declines there, so every
+ * rank reports the same fall-back (sum_path 2) and the ranks need not agree on anything beforehand;
+ * "epilogue_bias": test hook (1.0), scales the fixed-order sum from which the levels are derived while the chain is still
+ * running (a disagreement with the levels of the chained sum must be caught: fused_miss 2); "xchg_timeout_s": how long the in-kernel
  * peer exchange waits for a rank before ALL ranks give up (default 30)).  Returns PAPR_ERR_ARG for an unknown name. */
 int  papr_engine_set(papr_engine *e, const char *name, double value);
 
