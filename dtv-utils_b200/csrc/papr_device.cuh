@@ -236,11 +236,24 @@ int papr_seqsum_configure(void);
 void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, float sigmas, float bias, int fine_slots,
                              PaprPlan *plan, unsigned *fine_base, PaprPeers pp, unsigned long long seq, cudaStream_t s,
                              int ncells_max = PAPR_NCELLS_MAX);
-void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, unsigned long long n, PaprTables t, int graph,
-                                   PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv,
-                                   unsigned long long *status_word, PaprPlan *plan, PaprPeers pp,
-                                   unsigned long long seq, cudaStream_t s, PaprDevStats *parts_out = nullptr,
-                                   double bias = 1.0 /* test hook: scales the sum the levels are derived from */);
+// sharded: the statistics exchange + levels (papr_finalize.cuh: finalize_levels_x_body)
+struct PaprFinalizeXArgs {
+    const PaprCtaPartial *wp;
+    int nctas;
+    unsigned long long n;
+    PaprDevStats *local;
+    PaprTables tb;
+    int graph;
+    PaprDevStats *merged;
+    PaprDevLevels *lv;
+    unsigned long long *status_word;
+    PaprPlan *plan;
+    PaprPeers pp;
+    unsigned long long seq;
+    double bias; // test hook (1.0): scales the sum the levels are derived from
+};
+
+void papr_launch_finalize_levels_x(const PaprFinalizeXArgs &a, cudaStream_t s);
 void papr_launch_counts_x(unsigned long long *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp,
                           unsigned long long seq, cudaStream_t s);
 void papr_launch_tr(float *x, int nsym, int n, const float *kernel, const int *tone, int ntones, float vclip, int iterations,
@@ -250,7 +263,8 @@ void papr_launch_scan_tma(const void *tensor_map /* CUtensorMap */, int grid, co
                           cudaStream_t s);
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles,
                             const PaprTileRun *multi_tile, PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s,
-                            unsigned long long *zero_word = nullptr /* status word of the counts that follow */);
+                            unsigned long long *zero_word = nullptr /* status word of the counts that follow */,
+                            const PaprFinalizeXArgs *fx = nullptr /* sharded: one extra CTA runs the statistics exchange */);
 // single shard: chain (CTA 0) side by side with finalize + levels + counts from the fixed-order sum (the other CTAs)
 struct PaprEpilogueArgs {
     const PaprCtaPartial *wp;
@@ -265,6 +279,7 @@ struct PaprEpilogueArgs {
     const unsigned *fine_base;
     const unsigned long long *g_hist, *g_fine, *g_over;
     unsigned long long *counts, *status_word;
+    unsigned *done;                    // sharded: counting CTAs that have finished (the last one exchanges the counts)
     int *chain_report;                 // {XT_* status, why}
     double *chain_exact;               // the chained sequential sum (valid when status == XT_OK)
 };
@@ -273,7 +288,8 @@ void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *su
                                const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
                                const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
                                unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s,
-                               int decline /* this rank has no runs: publish an empty list marked XT_FALLBACK */);
+                               int decline /* this rank has no runs: publish an empty list marked XT_FALLBACK */,
+                               unsigned long long seq_counts /* of the counts exchange in the kernel's tail */);
 void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run, const int *tile_code,
                              const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles, const float *iq,
                              unsigned long long nsamples, PaprChainList *out, const PaprEpilogueArgs &a, int grid, cudaStream_t s);

@@ -251,6 +251,7 @@ struct papr_engine {
     unsigned *d_xt_multi_count = nullptr;
     PaprChainList *d_xt_chain = nullptr;
     PaprDevStats *d_xt_parts = nullptr;  // sharded: every rank's pass-1 state, in rank order
+    unsigned *d_epi_done = nullptr;      // sharded epilogue: counting CTAs finished (self-resetting)
     int xt_status = -1, xt_why = 0;      // of the last analysis (-1: the device chain did not run)
     // device work buffers
     int grid = 0;
@@ -367,6 +368,8 @@ static int engine_init(papr_engine *e, int device)
     CU(cudaMalloc(&e->d_xt_chain, sizeof(PaprChainList)));
     CU(cudaMemset(e->d_xt_chain, 0, sizeof(PaprChainList)));
     CU(cudaMalloc(&e->d_xt_parts, sizeof(PaprDevStats) * PAPR_XCHG_MAX_RANKS));
+    CU(cudaMalloc(&e->d_epi_done, sizeof(unsigned)));
+    CU(cudaMemset(e->d_epi_done, 0, sizeof(unsigned)));
     {
         std::vector<double> t(4 * PAPR_MAX_LEVELS, INFINITY);
         papr_host_build_tables(0, kLevels1dB, &t[0], &t[2 * PAPR_MAX_LEVELS]);
@@ -412,7 +415,7 @@ extern "C" void papr_engine_destroy(papr_engine *e)
     if (e->h_tile_data) cudaFreeHost(e->h_tile_data);
     cudaFree(e->d_pre4); cudaFree(e->d_tables); cudaFree(e->d_buf);
     cudaFree(e->d_xt_run); cudaFree(e->d_xt_code); cudaFree(e->d_xt_super); cudaFree(e->d_xt_hyper); cudaFree(e->d_xt_multi); cudaFree(e->d_xt_multi_tile);
-    cudaFree(e->d_xt_multi_count); cudaFree(e->d_xt_chain); cudaFree(e->d_xt_parts);
+    cudaFree(e->d_xt_multi_count); cudaFree(e->d_xt_chain); cudaFree(e->d_xt_parts); cudaFree(e->d_epi_done);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_stage[0]) cudaFreeHost(e->h_stage[0]);
     for (auto &ev : e->stage_done) if (ev) cudaEventDestroy(ev);
@@ -584,6 +587,7 @@ static PaprEpilogueArgs epilogue_args(papr_engine *e, u64 n, int graph)
     a.g_hist = e->d_work->hist; a.g_fine = e->d_fine; a.g_over = &e->d_work->over;
     a.counts = e->d_out->counts; a.status_word = &e->d_out->counts[PAPR_MAX_LEVELS];
     a.chain_report = e->d_out->chain; a.chain_exact = &e->d_out->chain_exact;
+    a.done = e->d_epi_done;
     return a;
 }
 
@@ -1409,25 +1413,26 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     papr_launch_zero_fine(&e->d_out->plan, e->d_fine, e->num_sms * 4, e->stream);
     e->launches += 3;
     const unsigned ntiles = (unsigned)((n + XT_TILE_SAMPLES - 1) / XT_TILE_SAMPLES);
-    if (chained) {
+    // every rank's pass-1 state -> merged statistics and the levels of the merged FIXED-ORDER sums ...
+    PaprFinalizeXArgs fx;
+    fx.wp = e->d_work->wp; fx.nctas = e->grid; fx.n = n; fx.local = &e->d_out->local; fx.tb = e->tables(graph); fx.graph = graph;
+    fx.merged = &e->d_out->merged; fx.lv = &e->d_out->lv; fx.status_word = &e->d_out->counts[PAPR_MAX_LEVELS];
+    fx.plan = &e->d_out->plan; fx.pp = e->peers; fx.seq = ++e->xseq[XK_STATS]; fx.bias = e->epilogue_bias;
+    if (chained) { // ... as one extra CTA of the kernel that composes the tile runs
         if ((rc = enqueue_scan_tma(e, d_iq, n, first, true))) return rc;
         const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES, nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
         papr_launch_xt_compose(e->d_xt_run, e->d_xt_code, ntiles, e->d_xt_multi_tile, e->d_xt_super, e->d_xt_hyper,
-                               (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream);
-        e->launches += 1;
+                               (int)std::min<unsigned>(nhyper, (unsigned)e->num_sms * 2), e->stream, nullptr, &fx);
     } else {
         if ((rc = enqueue_scan(e, true, true, d_iq, n, first, true))) return rc;
+        papr_launch_finalize_levels_x(fx, e->stream);
     }
-    // every rank's pass-1 state -> merged statistics and the levels of the merged FIXED-ORDER sums ...
-    papr_launch_finalize_levels_x(e->d_work->wp, e->grid, n, e->tables(graph), graph, &e->d_out->local, &e->d_out->merged,
-                                  &e->d_out->lv, &e->d_out->counts[PAPR_MAX_LEVELS], &e->d_out->plan, e->peers,
-                                  ++e->xseq[XK_STATS], e->stream, nullptr, e->epilogue_bias);
+    e->launches += 1;
     // ... then the chain (with its exchange) side by side with this shard's counts against those levels
     papr_launch_xt_epilogue_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
                               d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], epilogue_args(e, n, graph),
-                              e->num_sms, e->stream, chained ? 0 : 1);
-    papr_launch_counts_x(e->d_out->counts, &e->d_out->lv, &e->d_out->plan, e->peers, ++e->xseq[XK_COUNTS], e->stream);
-    e->launches += 3;
+                              e->num_sms, e->stream, chained ? 0 : 1, ++e->xseq[XK_COUNTS]); // (counts exchange in its tail)
+    e->launches += 2;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));

@@ -23,6 +23,7 @@
 
 #include "papr_scan_common.cuh"
 #include "papr_xchg.cuh"
+#include "papr_finalize.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // helpers
@@ -477,14 +478,21 @@ __device__ __forceinline__ PaprTileRun xt_pick(const PaprSuperRec &r, int k) // 
 
 __global__ void __launch_bounds__(1024) papr_xt_compose_kernel(const PaprTileRun *tile_run, const int *tile_code,
                                                                unsigned ntiles, const PaprTileRun *multi_tile,
-                                                               PaprSuperRec *super, PaprSuperRec *hyper, u64 *zero_word)
+                                                               PaprSuperRec *super, PaprSuperRec *hyper, u64 *zero_word,
+                                                               int ncompose, const PaprFinalizeXArgs fx)
 {
+    // sharded: one extra CTA exchanges the shards' pass-1 states and derives the levels meanwhile (it spins for the
+    // other ranks; the composing CTAs neither wait for it nor are waited for)
+    if ((int)blockIdx.x >= ncompose) {
+        finalize_levels_x_body(fx);
+        return;
+    }
     __shared__ PaprSuperRec s_rec[32];
     if (zero_word && blockIdx.x == 0 && threadIdx.x == 0) *zero_word = 0; // the status word of the counts that follow (RES_* bits are OR-ed in)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES;
     const unsigned nhyper = (nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
-    for (unsigned hy = blockIdx.x; hy < nhyper; hy += gridDim.x) {
+    for (unsigned hy = blockIdx.x; hy < nhyper; hy += (unsigned)ncompose) {
         const unsigned st = hy * XT_HYPER_SUPERS + warp;
         {
             const unsigned t = st * XT_SUPER_TILES + lane;
@@ -548,9 +556,12 @@ __global__ void __launch_bounds__(1024) papr_xt_compose_kernel(const PaprTileRun
 }
 
 void papr_launch_xt_compose(const PaprTileRun *tile_run, const int *tile_code, unsigned ntiles, const PaprTileRun *multi_tile,
-                            PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s, unsigned long long *zero_word)
+                            PaprSuperRec *super, PaprSuperRec *hyper, int grid, cudaStream_t s, unsigned long long *zero_word,
+                            const PaprFinalizeXArgs *fx)
 {
-    papr_xt_compose_kernel<<<grid, 1024, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super, hyper, zero_word);
+    PaprFinalizeXArgs none = {};
+    papr_xt_compose_kernel<<<grid + (fx ? 1 : 0), 1024, 0, s>>>(tile_run, tile_code, ntiles, multi_tile, super, hyper, zero_word,
+                                                                grid, fx ? *fx : none);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1247,12 +1258,22 @@ void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *supe
 // the ranks is needed beforehand, and the exchange sequence is the same whatever the shard sizes are.
 __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c, PaprChainList *out, PaprPlan *plan,
                                                                        PaprPeers pp, u64 seq, const PaprEpilogueArgs a,
-                                                                       int decline)
+                                                                       int decline, u64 seq_counts)
 {
     if (blockIdx.x != 0) {
         const PaprDevLevels *lv = a.lv;
-        xt_count_levels(a, min(max(lv->L, 0), PAPR_MAX_LEVELS), (int)blockIdx.x - 1, (int)gridDim.x - 1,
-                        [&](int j) { return lv->level[j]; });
+        const int L = min(max(lv->L, 0), PAPR_MAX_LEVELS);
+        xt_count_levels(a, L, (int)blockIdx.x - 1, (int)gridDim.x - 1, [&](int j) { return lv->level[j]; });
+        // the counting CTA that finishes last exchanges the counts with the other ranks (no separate launch)
+        __shared__ unsigned s_ticket;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(a.done, 1u);
+        __syncthreads();
+        if (s_ticket == gridDim.x - 2) {
+            if (threadIdx.x == 0) *a.done = 0; // ready for the next launch
+            xchg_counts(a.counts, L, plan, pp, seq_counts);
+        }
         return;
     }
     __shared__ XtShared sh;
@@ -1310,11 +1331,12 @@ __global__ void __launch_bounds__(XT_CHAIN_T) papr_xt_epilogue_x_kernel(XtCtx c,
 void papr_launch_xt_epilogue_x(const PaprSuperRec *hyper, const PaprSuperRec *super, const PaprTileRun *tile_run,
                                const int *tile_code, const PaprTileRun *multi, const PaprTileRun *multi_tile, unsigned ntiles,
                                const float *iq, unsigned long long nsamples, PaprChainList *out, PaprPlan *plan, PaprPeers pp,
-                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s, int decline)
+                               unsigned long long seq, const PaprEpilogueArgs &a, int grid, cudaStream_t s, int decline,
+                               unsigned long long seq_counts)
 {
     XtCtx c;
     c.hyper = hyper; c.super = super; c.tile_run = tile_run; c.tile_code = tile_code; c.multi = multi; c.multi_tile = multi_tile;
     c.ntiles = ntiles; c.nsuper = (ntiles + XT_SUPER_TILES - 1) / XT_SUPER_TILES; c.iq = iq; c.nsamples = nsamples;
     c.nhyper = (c.nsuper + XT_HYPER_SUPERS - 1) / XT_HYPER_SUPERS;
-    papr_xt_epilogue_x_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq, a, decline);
+    papr_xt_epilogue_x_kernel<<<grid < 2 ? 2 : grid, XT_CHAIN_T, 0, s>>>(c, out, plan, pp, seq, a, decline, seq_counts);
 }

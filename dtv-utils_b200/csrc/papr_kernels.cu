@@ -160,98 +160,7 @@ void papr_launch_scan(bool stats, bool hist, int grid, const PaprScanArgs &a, cu
 // ------------------------------------------------------------------------------------------------
 // pass-1 follow-ups
 // ------------------------------------------------------------------------------------------------
-#define FIN_T 256
-// fixed-order reduction of the CTA partials (sum) and (value desc, index asc) selection; result in
-// thread 0 of the calling CTA
-__device__ void reduce_partials(const PaprCtaPartial *wp, int nctas, u64 n, PaprDevStats *out)
-{
-    __shared__ double s_sum[FIN_T];
-    __shared__ int s_val[PAPR_NTRACK][FIN_T];
-    __shared__ u64 s_idx[PAPR_NTRACK][FIN_T];
-    const int t = threadIdx.x;
-    double sum = 0.0;
-    int val[PAPR_NTRACK];
-    u64 idx[PAPR_NTRACK];
-    for (int k = 0; k < PAPR_NTRACK; ++k) { val[k] = 0; idx[k] = 0; }
-    for (int i = t; i < nctas; i += FIN_T) {
-        sum += wp[i].sum;
-        for (int k = 0; k < PAPR_NTRACK; ++k)
-            if (wp[i].val[k] > 0 && better(wp[i].val[k], wp[i].idx[k], val[k], idx[k])) {
-                val[k] = wp[i].val[k];
-                idx[k] = wp[i].idx[k];
-            }
-    }
-    s_sum[t] = sum;
-    for (int k = 0; k < PAPR_NTRACK; ++k) { s_val[k][t] = val[k]; s_idx[k][t] = idx[k]; }
-    __syncthreads();
-    for (int o = FIN_T / 2; o > 0; o >>= 1) {
-        if (t < o) {
-            s_sum[t] += s_sum[t + o];
-            for (int k = 0; k < PAPR_NTRACK; ++k)
-                if (s_val[k][t + o] > 0 && better(s_val[k][t + o], s_idx[k][t + o], s_val[k][t], s_idx[k][t])) {
-                    s_val[k][t] = s_val[k][t + o];
-                    s_idx[k][t] = s_idx[k][t + o];
-                }
-        }
-        __syncthreads();
-    }
-    if (t == 0) {
-        out->sum = s_sum[0];
-        out->n = n;
-        for (int k = 0; k < PAPR_NTRACK; ++k) { out->val[k] = s_val[k][0]; out->idx[k] = s_idx[k][0]; }
-        out->flags = isfinite(s_sum[0]) ? 0u : PAPR_FLAG_NONFINITE;
-    }
-}
-
-// Merge the shards' pass-1 states in rank (= index) order and evaluate the reference's scalar
-// epilogue on the device:  avg = sum/offset (papr.c:131), ratio = peak/avg, L, and
-// level[j] = (float)(pow(10, x_j) * avg) (papr.c:139 / 170).  pow(10, x_j) and the least ratio for
-// which the reference's loops reach level j are tabulated once with the HOST libm, so only IEEE
-// double multiply/divide/compare and one rounding to float happen here - bit-identical to the host.
-__device__ void merge_and_levels(const PaprDevStats *parts, int nparts, const PaprTables &tb, int graph,
-                                 PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
-                                 size_t stride_bytes = sizeof(PaprDevStats), const PaprChainList *chain = nullptr,
-                                 int *chain_report = nullptr, double bias = 1.0 /* test hook: scales the sum the levels come from */)
-{
-    __shared__ int s_L;
-    __shared__ double s_avg;
-    if (threadIdx.x == 0) {
-        PaprDevStats m = parts[0];
-        for (int p = 1; p < nparts; ++p) {
-            const PaprDevStats q = *reinterpret_cast<const PaprDevStats *>(reinterpret_cast<const char *>(parts) + p * stride_bytes);
-            m.sum += q.sum;
-            m.n += q.n;
-            for (int k = 0; k < PAPR_NTRACK; ++k)
-                if (q.val[k] > m.val[k]) { m.val[k] = q.val[k]; m.idx[k] = q.idx[k]; } // strict: earlier shard wins ties
-            m.flags |= q.flags;
-        }
-        if (!isfinite(m.sum)) m.flags |= PAPR_FLAG_NONFINITE;
-        if (chain) { // the sequential sum chained over all shards on the device replaces the approximate one
-            const int st = chain->status;
-            if (st == XT_OK) m.sum = chain->exact;
-            chain_report[0] = st;
-            chain_report[1] = chain->why;
-        }
-        *merged = m;
-        double avg = __ddiv_rn(__dmul_rn(m.sum, bias), (double)(long long)m.n);
-        double ratio = __ddiv_rn((double)__int_as_float(m.val[TR_PEAK]), avg);
-        int lo = 0, hi = tb.nlevels_max; // number of j with ratio >= ratio_min[j] (non-decreasing table)
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (ratio >= tb.ratio_min[mid]) lo = mid + 1; else hi = mid;
-        }
-        lv->avg = avg;
-        lv->ratio = ratio;
-        lv->L = lo;
-        lv->graph = graph;
-        *status_word = 0; // RES_* bits of the resolve that follows
-        s_L = lo;
-        s_avg = avg;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < s_L; j += blockDim.x)
-        lv->level[j] = __double2float_rn(__dmul_rn(tb.pow10[j], s_avg));
-}
+#include "papr_finalize.cuh"
 
 // one CTA.  with_levels: single-shard analysis, the local state IS the merged state.
 __global__ void __launch_bounds__(FIN_T) papr_stats_finalize_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
@@ -684,67 +593,26 @@ void papr_launch_plan_pred_x(const double *cta_pre, int nctas, PaprTables t, flo
     papr_plan_pred_x_kernel<<<1, 1024, 0, s>>>(cta_pre, nctas, t, sigmas, bias, fine_slots, plan, fine_base, pp, seq, ncells_max);
 }
 
-// sharded: CTA partials -> this shard's pass-1 state -> published; every rank's state collected and
-// merged in rank order (first occurrence preserved); avg, L and the level table of the WHOLE capture
-__global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const PaprCtaPartial *wp, int nctas, u64 n,
-                                                                      PaprDevStats *local, PaprTables tb, int graph,
-                                                                      PaprDevStats *merged, PaprDevLevels *lv,
-                                                                      u64 *status_word, PaprPlan *plan, PaprPeers pp,
-                                                                      u64 seq, PaprDevStats *parts_out, double bias)
+// sharded: CTA partials -> this shard's pass-1 state -> published; every rank's state collected and merged in rank
+// order; avg, L and the level table of the WHOLE capture (papr_finalize.cuh: finalize_levels_x_body).  Stand-alone
+// launch for shards that do not chain the sequential sum; otherwise the extra CTA of papr_xt_compose_kernel does it.
+__global__ void __launch_bounds__(FIN_T) papr_finalize_levels_x_kernel(const PaprFinalizeXArgs a)
 {
-    reduce_partials(wp, nctas, n, local);
-    __threadfence();
-    __syncthreads(); // thread 0's *local is visible to the CTA
-    xchg_publish(pp, XK_STATS, offsetof(PaprXchgSlot, stats), reinterpret_cast<const u64 *>(local),
-                 (int)(sizeof(PaprDevStats) / 8), seq);
-    const bool ok = xchg_wait(pp, XK_STATS, seq);
-    if (!ok && threadIdx.x == 0) plan->pad = 1;
-    __shared__ PaprDevStats s_parts[PAPR_XCHG_MAX_RANKS];
-    for (int i = threadIdx.x; i < pp.world * (int)(sizeof(PaprDevStats) / 8); i += blockDim.x) {
-        const int q = i / (int)(sizeof(PaprDevStats) / 8), w = i % (int)(sizeof(PaprDevStats) / 8);
-        reinterpret_cast<u64 *>(&s_parts[q])[w] = ld_volatile(reinterpret_cast<const u64 *>(&pp.win[pp.rank]->slot[q].stats) + w);
-    }
-    __syncthreads();
-    if (parts_out) // the chain that follows needs every shard's approximate sum
-        for (int i = threadIdx.x; i < pp.world * (int)(sizeof(PaprDevStats) / 8); i += blockDim.x)
-            reinterpret_cast<u64 *>(parts_out)[i] = reinterpret_cast<const u64 *>(s_parts)[i];
-    // (chained: these levels come from the fixed-order sums; the host checks them against the chained sum's)
-    merge_and_levels(s_parts, pp.world, tb, graph, merged, lv, status_word, sizeof(PaprDevStats), nullptr, nullptr, bias);
+    finalize_levels_x_body(a);
 }
 
-void papr_launch_finalize_levels_x(const PaprCtaPartial *wp, int nctas, u64 n, PaprTables t, int graph,
-                                   PaprDevStats *local, PaprDevStats *merged, PaprDevLevels *lv, u64 *status_word,
-                                   PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s, PaprDevStats *parts_out, double bias)
+void papr_launch_finalize_levels_x(const PaprFinalizeXArgs &a, cudaStream_t s)
 {
-    papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(wp, nctas, n, local, t, graph, merged, lv, status_word, plan, pp, seq,
-                                                      parts_out, bias);
+    papr_finalize_levels_x_kernel<<<1, FIN_T, 0, s>>>(a);
 }
 
-// sharded: publish this shard's level counts (+ status word), collect every rank's, add them up.
-// Only the L levels in use (and the status word) travel; buffer seq & 1 of the slot is written, so a
-// second publication within one analysis (exact redo after a fused miss) cannot race with a peer that
-// is still summing the first.
+// sharded: publish this shard's level counts (+ status word), collect every rank's, add them up (papr_xchg.cuh).
+// Stand-alone launch for the recount / exact-redo paths; the first exchange of an analysis happens in the tail of
+// papr_xt_epilogue_x_kernel.
 __global__ void __launch_bounds__(1024) papr_counts_x_kernel(u64 *counts, const PaprDevLevels *lv, PaprPlan *plan,
                                                              PaprPeers pp, u64 seq)
 {
-    const int L = min(max(lv->L, 0), PAPR_MAX_LEVELS), buf = (int)(seq & 1);
-    const size_t off = offsetof(PaprXchgSlot, counts) + (size_t)buf * sizeof(u64) * (PAPR_MAX_LEVELS + 1);
-    for (int r = 0; r < pp.world; ++r) {
-        u64 *dst = reinterpret_cast<u64 *>(reinterpret_cast<char *>(&pp.win[r]->slot[pp.rank]) + off);
-        for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = counts[i];
-        if (threadIdx.x == 0) dst[PAPR_MAX_LEVELS] = counts[PAPR_MAX_LEVELS];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->flag[XK_COUNTS][pp.rank], seq);
-    const bool ok = xchg_wait(pp, XK_COUNTS, seq);
-    if (!ok && threadIdx.x == 0) plan->pad = 1;
-    for (int i = threadIdx.x; i <= PAPR_MAX_LEVELS; i += blockDim.x) {
-        if (i >= L && i != PAPR_MAX_LEVELS) continue;
-        u64 acc = 0;
-        for (int q = 0; q < pp.world; ++q) acc += ld_volatile(&pp.win[pp.rank]->slot[q].counts[buf][i]);
-        counts[i] = acc;
-    }
+    xchg_counts(counts, min(max(lv->L, 0), PAPR_MAX_LEVELS), plan, pp, seq);
 }
 
 void papr_launch_counts_x(u64 *counts, const PaprDevLevels *lv, PaprPlan *plan, PaprPeers pp, u64 seq, cudaStream_t s)

@@ -71,3 +71,29 @@ static __device__ bool xchg_wait(const PaprPeers &pp, int kind, u64 seq)
     return !late;
 }
 
+
+// All threads of ONE CTA: publish this shard's level counts (+ status word), collect every rank's, add them up in
+// place.  Only the L levels in use (and the status word) travel; buffer seq & 1 of the slot is written, so a second
+// publication within one analysis (recount / exact redo) cannot race with a peer that is still summing the first.
+// `counts` may have been written by other CTAs of the calling kernel (after a __threadfence + ticket): read past L1.
+static __device__ void xchg_counts(u64 *counts, int L, PaprPlan *plan, const PaprPeers &pp, u64 seq)
+{
+    const int buf = (int)(seq & 1);
+    const size_t off = offsetof(PaprXchgSlot, counts) + (size_t)buf * sizeof(u64) * (PAPR_MAX_LEVELS + 1);
+    for (int r = 0; r < pp.world; ++r) {
+        u64 *dst = reinterpret_cast<u64 *>(reinterpret_cast<char *>(&pp.win[r]->slot[pp.rank]) + off);
+        for (int i = threadIdx.x; i < L; i += blockDim.x) dst[i] = ld_volatile(&counts[i]);
+        if (threadIdx.x == 0) dst[PAPR_MAX_LEVELS] = ld_volatile(&counts[PAPR_MAX_LEVELS]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pp.world) st_release_sys(&pp.win[threadIdx.x]->flag[XK_COUNTS][pp.rank], seq);
+    const bool ok = xchg_wait(pp, XK_COUNTS, seq);
+    if (!ok && threadIdx.x == 0) plan->pad = 1;
+    for (int i = threadIdx.x; i <= PAPR_MAX_LEVELS; i += blockDim.x) {
+        if (i >= L && i != PAPR_MAX_LEVELS) continue;
+        u64 acc = 0;
+        for (int q = 0; q < pp.world; ++q) acc += ld_volatile(&pp.win[pp.rank]->slot[q].counts[buf][i]);
+        counts[i] = acc;
+    }
+}
