@@ -1432,7 +1432,7 @@ extern "C" int papr_shard_analyze_p2p(papr_engine *e, const float *d_iq, uint64_
     papr_launch_xt_epilogue_x(e->d_xt_hyper, e->d_xt_super, e->d_xt_run, e->d_xt_code, e->d_xt_multi, e->d_xt_multi_tile, ntiles,
                               d_iq, n, e->d_xt_chain, &e->d_out->plan, e->peers, ++e->xseq[XK_CHAIN], epilogue_args(e, n, graph),
                               e->num_sms, e->stream, chained ? 0 : 1, ++e->xseq[XK_COUNTS]); // (counts exchange in its tail)
-    e->launches += 2;
+    e->launches += 1;
     if ((rc = enqueue_fetch(e))) return rc;
     CU(cudaEventRecord(e->ev_end, e->stream));
     CU(cudaStreamSynchronize(e->stream));
