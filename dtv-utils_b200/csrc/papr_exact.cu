@@ -1251,8 +1251,9 @@ void papr_launch_xt_epilogue(const PaprSuperRec *hyper, const PaprSuperRec *supe
 // every peer's window over NVLink, collects the others', and walks ALL lists in rank order from a running sum
 // of 0: the same work and the same verdict on every rank, no hand-over from GPU to GPU.
 // With the level counts side by side, as in the single-shard epilogue: CTA 0 is the chain; the other CTAs count
-// this shard's samples above the levels that papr_finalize_levels_x_kernel has just derived from the merged
-// FIXED-ORDER sums (a.lv) - the host verifies those levels against the ones of the chained sum afterwards.
+// this shard's samples above the levels that the statistics exchange (the extra CTA of papr_xt_compose_kernel, or
+// papr_finalize_levels_x_kernel) has just derived from the merged FIXED-ORDER sums (a.lv) - the host verifies those
+// levels against the ones of the chained sum afterwards; the counting CTA that finishes last exchanges the counts.
 // decline != 0: this rank's sweep produced no runs (shard too small for the TMA-fed sweep, or the exact sum is switched
 // off): it publishes an empty list marked XT_FALLBACK, so that EVERY rank reports the fall-back - no agreement between
 // the ranks is needed beforehand, and the exchange sequence is the same whatever the shard sizes are.
