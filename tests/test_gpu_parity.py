@@ -288,6 +288,36 @@ def test_full_size_properties(built, eng, torch_cuda, log2n):
     assert built.format_result(head) == _gold("appA_1M", False)
 
 
+def test_two_launch_shard_32gib_fused_equals_two_pass(built, eng, torch_cuda):
+    """32 GiB per GPU (BASELINE configs[2] / [3]: 2^32 samples = two launches of the sweep, tile records and the
+    chain spanning both): the one-sweep analysis with the sequential sum chained on the device must print what the
+    two-pass schedule prints, whose sum comes from the independent two-sweep emulation - text and sum bits."""
+    import struct
+    free, _total = torch_cuda.cuda.mem_get_info()
+    n = 1 << 32
+    if free < 8 * n + (4 << 30):
+        pytest.skip("needs 36 GiB of free HBM")
+    d = torch_cuda.empty(2 * n, dtype=torch_cuda.float32, device="cuda:0")
+    eng.siggen(d, 0, n, 2)
+    try:
+        for graph in (False, True):
+            eng.set("mode", 2)
+            a = eng.analyze_device(d, n, graph)
+            eng.set("mode", 1)
+            b = eng.analyze_device(d, n, graph)
+            assert (a.sum_path & 0xff) == 1 and a.fused_miss in (0, 2), (a.sum_path, a.fused_miss)
+            assert (b.sum_path & 0xff) == 2
+            assert struct.pack("<d", a.stats.sum) == struct.pack("<d", b.stats.sum)
+            assert a.stats.as_tuple() == b.stats.as_tuple() and a.counts() == b.counts()
+            assert built.format_result(a) == built.format_result(b)
+            c = a.counts()
+            assert all(x >= y for x, y in zip(c, c[1:])) and 0 < c[0] < n and c[-1] >= 1
+    finally:
+        eng.set("mode", 0)
+        del d
+        torch_cuda.cuda.empty_cache()
+
+
 # ---- BASELINE configs[1] at full size against the REAL reference binary ------------------------------
 def test_config1_4gib_cli_vs_reference_binary(built, eng, torch_cuda, tmp_path_factory):
     """`papr` on a 4 GiB synthetic capture (2^29 samples, seed 1): stdout of the drop-in CLI must be
