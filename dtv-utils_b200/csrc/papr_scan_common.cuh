@@ -115,11 +115,11 @@ __device__ __forceinline__ unsigned hist_bump(unsigned addr)
     return fb;
 }
 
-// one more per-value counter, predicated (no branch): fb = 1 + first fine-table counter of the sample's cell, 0 = none
+// one more per-value counter: fb = 1 + first fine-table counter of the sample's cell (never 0 here)
 __device__ __forceinline__ void fine_bump(unsigned long long *g_fine, unsigned fb, unsigned bits, unsigned fmask)
 {
-    unsigned long long *p = g_fine + (fb - 1u + (bits & fmask)); // (never dereferenced when fb == 0)
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t@p red.global.add.u64 [%1], 1;\n\t}" ::"r"(fb), "l"(p) : "memory");
+    unsigned long long *p = g_fine + (fb - 1u + (bits & fmask));
+    asm volatile("red.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
 }
 
 // the two samples of one 16-byte load
@@ -129,10 +129,15 @@ __device__ __forceinline__ void hist_pair(ScanState<STATS, HIST> &st, float v0, 
     const unsigned b0 = __float_as_uint(v0), b1 = __float_as_uint(v1);
     const unsigned f0 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b0));
     const unsigned f1 = hist_bump<FB_OFF>(hist_slot<STATS, HIST, SH>(st, b1));
-    if (f0 | f1) { // a lane in a cell that may hold a threshold: count it per value.  (A per-lane branch on purpose: a
-                   // vote would make it warp-uniform but costs more - ptxas guards every *_sync vote with a BRA.DIV.)
-        fine_bump(st.g_fine, f0, b0, st.fmask);
-        fine_bump(st.g_fine, f1, b1, st.fmask);
+    // A lane in a cell that may hold a threshold counts the sample per value.  A per-lane branch on purpose (a vote
+    // would make it warp-uniform but costs more: ptxas guards every *_sync vote with a BRA.DIV), and only the lanes
+    // that have such a sample enter: inside, the first update needs no predicate, and a lane with two of them (rare)
+    // takes one more branch - about a third fewer instructions than two predicated updates (-g takes this path for
+    // every second pair of a warp).
+    if (f0 | f1) {
+        const bool first = f0 != 0;
+        fine_bump(st.g_fine, first ? f0 : f1, first ? b0 : b1, st.fmask);
+        if (first && f1 != 0) fine_bump(st.g_fine, f1, b1, st.fmask);
     }
 }
 

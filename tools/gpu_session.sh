@@ -1,11 +1,6 @@
 #!/bin/bash
-# what the last 1-GPU gpurun call of the development loop ran; outputs land in gpurun_out/
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-nvidia-smi -L > $O/gpu.txt 2>&1
-echo "== pytest -m gpu"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/pytest_gpu.txt
-echo "== smoke"
-timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2
-echo "== bench"
-timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 300 $O/bench_n1.json
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "device_path or seeded or full_size or epilogue or two_launch or bsearch or forced_miss or chunk_boundary or host_buffer" 2>&1 | tail -5 | tee $O/pytest_subset.txt
+timeout 90 python tools/ab_probe.py - 2>&1 | tail -2 | tee $O/ab_tree2.txt
+timeout 90 python tools/ab_probe.py - 2>&1 | tail -2 | tee -a $O/ab_tree2.txt
