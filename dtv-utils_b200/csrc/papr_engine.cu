@@ -1319,7 +1319,7 @@ extern "C" int papr_shard_finish(papr_engine *e, int graph, papr_result *out)
 
 // ------------------------------------------------------------------------------------------------
 // sharded analysis with the exchanges fused into the kernels over peer memory (NVLink): one call per
-// rank, the same five-kernel chain as the single-GPU fused analysis plus one tiny summing kernel
+// rank, the same six launches as the single-GPU fused analysis
 // ------------------------------------------------------------------------------------------------
 extern "C" int papr_xchg_export(papr_engine *e, void *handle64)
 {

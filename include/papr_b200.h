@@ -197,7 +197,8 @@ int papr_shard_counts_async(papr_engine *e, const void *d_all_stats, int nparts,
                             const float *d_iq, uint64_t nsamples);
 int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
 
-/* The same sharded analysis with the three exchanges fused INTO the kernels over peer memory (NVLink,
+/* The same sharded analysis with the four exchanges (presample, pass-1 states, the chain of the sequential
+ * sum, level counts) fused INTO the kernels over peer memory (NVLink,
  * one process per GPU): every engine owns a small window in device memory that the other ranks map
  * with cudaIpc; the producing kernel stores its values into every peer's window and raises a flag,
  * the consuming kernel polls its own window - no collective launches in between.
@@ -206,7 +207,10 @@ int papr_shard_finish(papr_engine *e, int graph, papr_result *out);
  *   papr_shard_analyze_p2p -> called by EVERY rank with its byte range; the whole-capture result on
  *              every rank.  Fused mode; on a miss every rank re-runs the exact pass (same decision
  *              everywhere, because the merged statistics and the summed status word are identical).
- * A rank that never calls leaves the others with PAPR_ERR_INTERNAL after a 4 s device-side timeout. */
+ *              Shards may differ in size; a rank whose shard cannot chain the sequential sum on the device
+ *              declines inside the exchange and every rank reports sum_path 2.
+ * A rank that never calls leaves ALL ranks (itself included, should it arrive late) with PAPR_ERR_INTERNAL
+ * after the device-side timeout (tunable "xchg_timeout_s", default 30 s). */
 int papr_xchg_export(papr_engine *e, void *handle64);
 int papr_xchg_attach(papr_engine *e, int rank, int world, const void *handles /* world x 64 bytes */);
 /* unmaps the peers' windows; detach on every rank, synchronise, THEN destroy the engines */
