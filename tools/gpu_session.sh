@@ -1,13 +1,11 @@
 #!/bin/bash
-# what the last 1-GPU gpurun call of the development loop ran; outputs land in gpurun_out/
+# what a 1-GPU gpurun call of the development loop runs (tests, smoke, bench); outputs land in gpurun_out/
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
+nvidia-smi -L > $O/gpu.txt 2>&1
+echo "== pytest -m gpu"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 | tee $O/pytest_gpu.txt
+echo "== smoke"
+timeout 120 python __graft_entry__.py smoke 2>&1 | tail -2
 echo "== bench"
-timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 200 $O/bench_n1.json
-echo "== ncu --set full, 1 dB and -g"
-bash tools/ncu_xt.sh 2>&1 | tail -2
-bash tools/ncu_xt.sh g 2>&1 | tail -2
-for m in 1dB g; do
-  ncu -i $O/r02_xt_$m.ncu-rep --page raw --csv > $O/r02_xt_${m}_raw.csv 2>/dev/null
-  rm -f $O/r02_xt_$m.ncu-rep
-done
+timeout 400 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; tail -c 300 $O/bench_n1.json
