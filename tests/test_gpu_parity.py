@@ -134,6 +134,27 @@ def test_chunk_boundary_cases_all_sources(built, eng, torch_cuda, tmp_path):
         eng.set("chunk_bytes", 64 << 20)
 
 
+def test_random_captures_host_and_device_paths(built, eng, torch_cuda):
+    """The 48 seeded captures of tests/test_oracle.py (pinned there to the reference binary: scales from denormal to
+    1e15, heavy tails, constant stretches, signed zeros, NaN / Inf, ragged lengths) through the host path and,
+    where the bytes are whole 16-byte-aligned samples, the device path in both schedules."""
+    from test_oracle import random_captures
+    try:
+        for k, img in random_captures():
+            for graph in (False, True):
+                want = oracle_binding.run_image(img, graph)
+                assert built.format_result(eng.analyze_host(img, graph=graph)) == want, (k, len(img), graph, "host")
+                if len(img) % 8 == 0 and len(img) >= 8:
+                    d = _dev(torch_cuda, np.frombuffer(img, np.float32))
+                    for mode in (1, 2):
+                        eng.set("mode", mode)
+                        got = built.format_result(eng.analyze_device(d, len(img) // 8, graph))
+                        assert got == want, (k, len(img), graph, mode)
+                    eng.set("mode", 0)
+    finally:
+        eng.set("mode", 0)
+
+
 def test_pinned_source_goes_direct(built, eng, torch_cuda):
     f = torch_cuda.from_numpy(fixtures.siggen(0, 300_000, 11)).pin_memory()
     res = eng.analyze_host(f, graph=True)

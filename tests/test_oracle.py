@@ -78,3 +78,49 @@ def test_oracle_equals_reference_binary_on_chunk_boundary_captures(tmp_path):
         for graph in (False, True):
             r = subprocess.run([ref] + (["-g"] if graph else []) + [str(p)], capture_output=True)
             assert r.stdout == oracle_binding.run_image(img, graph), (k, nf, graph)
+
+
+def random_captures(seed=20261017, count=48):
+    """Seeded small captures of very different character: scales from denormal to 1e15, heavy tails, constant and
+    all-zero stretches, signed zeros, NaN / Inf samples, ragged byte lengths."""
+    rng = np.random.default_rng(seed)
+    for k in range(count):
+        n = int(rng.integers(1, 6000))
+        kind = k % 8
+        if kind == 0:
+            f = rng.standard_normal(2 * n) * 10.0 ** rng.uniform(-22, 15)
+        elif kind == 1:
+            f = rng.uniform(-1, 1, 2 * n) * 10.0 ** rng.uniform(-3, 3)
+        elif kind == 2:  # heavy tail: a few huge samples among small ones (large PAPR, many levels)
+            f = rng.standard_normal(2 * n) * 1e-3
+            f[rng.integers(0, 2 * n, 3)] = rng.choice([-1.0, 1.0], 3) * 10.0 ** rng.uniform(0, 6, 3)
+        elif kind == 3:  # constant envelope / exact ties between extrema
+            f = np.tile(np.array([0.5, -0.5], np.float64) * rng.choice([1.0, 3.0, 0.1]), n)
+        elif kind == 4:  # zeros, then signal, signed zeros inside
+            f = rng.standard_normal(2 * n)
+            f[: 2 * (n // 2)] = 0.0
+            f[rng.integers(0, 2 * n, 4)] = -0.0
+        elif kind == 5:  # denormal powers
+            f = rng.standard_normal(2 * n) * 1e-21
+        elif kind == 6:  # a NaN or an Inf somewhere (the reference's prints become nan / inf)
+            f = rng.standard_normal(2 * n)
+            f[int(rng.integers(0, 2 * n))] = rng.choice([np.nan, -np.nan, np.inf, -np.inf])
+        else:  # small integers: exact powers, many equal samples
+            f = rng.integers(-4, 5, 2 * n).astype(np.float64)
+        img = f.astype(np.float32).tobytes()
+        yield k, img[: len(img) - int(rng.integers(0, 8))]  # 0-7 bytes short: lone I, ragged tails
+
+
+def test_oracle_equals_reference_binary_on_random_captures(tmp_path):
+    """Differential test of the restatement against the unmodified reference binary (oracle/_ref/papr) on 48
+    seeded captures x 2 modes - beyond the committed golden vectors."""
+    import subprocess
+    ref = os.path.join(oracle_binding.ORACLE_DIR, "_ref", "papr")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/papr not built")
+    for k, img in random_captures():
+        p = tmp_path / ("rnd%d.cfile" % k)
+        p.write_bytes(img)
+        for graph in (False, True):
+            r = subprocess.run([ref] + (["-g"] if graph else []) + [str(p)], capture_output=True, timeout=120)
+            assert r.stdout == oracle_binding.run_image(img, graph), (k, len(img), graph)
