@@ -100,7 +100,7 @@ __device__ __forceinline__ unsigned hist_slot(const ScanState<STATS, HIST> &st, 
     // a NaN power exceeds no level (`value > level[j]` is false, papr.c:148); only the stand-alone CCDF
     // pass can meet one with levels to count against - with the statistics in the same sweep the sum is
     // NaN too and the reference prints no levels at all
-    if (!STATS) c = bits > 0x7f800000u ? 0 : c;
+    if (!STATS) c = bits > 0x7f800000u ? -1 : c; // (-1 + neg_base1 = -cell_base <= 0: slot 0 whatever the plan's base is)
     const int slot = __viaddmin_s32_relu(c, st.neg_base1, st.ncells + 1); // max(min(c + neg_base1, ncells + 1), 0)
     return st.smem_slot0 + ((unsigned)slot << 2);
 }
