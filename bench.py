@@ -125,6 +125,24 @@ def time_cpu(path, nsamples, graph, repeats=1):
     return best, ("reference" if ref else "port"), out
 
 
+def host_info(value):
+    """host CPU model and core count beside the 1-thread figure, plus the hypothetical rate if every
+    core ran its own copy of the (single-threaded) tool on its own byte range - labelled as what it is."""
+    model = None
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    n = os.cpu_count() or 1
+    return {"host_cpus": n, "host_cpu_model": model,
+            "hypothetical_all_cores": {"value": value * n, "unit": UNIT,
+                                       "note": "1-thread rate x host_cpus; the reference tool has no threads"}}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -153,8 +171,7 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1 << args.log2_samples),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
-                             "host_cpus": os.cpu_count()},
+            "cpu_baseline": dict({"value": v, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}, **host_info(v)),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -504,9 +521,10 @@ def cpu_baseline(args, pinned, n_host, graph, eng, pb):
     finally:
         if os.path.exists(path):
             os.unlink(path)
-    return {"value": ns / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
-            "sample": "first 2^%d samples (%d MiB) of the same capture, file on tmpfs" % (ns.bit_length() - 1, ns * 8 >> 20),
-            "host_cpus": os.cpu_count(), "stdout_identical_to_gpu_on_sample": bool(same)}
+    v = ns / dt / 1e9
+    return dict({"value": v, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+                 "sample": "first 2^%d samples (%d MiB) of the same capture, file on tmpfs" % (ns.bit_length() - 1, ns * 8 >> 20),
+                 "stdout_identical_to_gpu_on_sample": bool(same)}, **host_info(v))
 
 
 def main():
